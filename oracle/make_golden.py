@@ -1,0 +1,182 @@
+"""TEST INFRASTRUCTURE ONLY -- writes tests/golden/*.npz by running the REAL reference (authoring container).
+
+    python oracle/make_golden.py            # needs /root/reference; re-creates every fixture
+
+The reference ships no golden vectors, so these fixtures -- outputs of the reference's own
+`Quantize`, `HRqVae.get_semantic_ids`, `SemanticIdUniquenessLoss`, `Kmeans` on seeded synthetic inputs
+ -- are what pins the oracle, and through it the CUDA path.  The fixtures travel to the GPU
+box; the reference does not.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.reference_shim import load_reference  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def unit_rows(n, d, gen):
+    return torch.nn.functional.normalize(torch.randn(n, d, generator=gen), dim=-1)
+
+
+def make_quantize_cases(ref):
+    """Single `Quantize.forward` (modules/quantize.py:100-154): value + autograd gradients."""
+    Q = ref.quantize
+    modes = {"ste": Q.QuantizeForwardMode.STE, "rot": Q.QuantizeForwardMode.ROTATION_TRICK}
+    out = {}
+    for mname, mode in modes.items():
+        for normalize in (False, True):
+            for training in (True, False):
+                gen = torch.Generator().manual_seed(11)
+                n, d, k, beta = 48, 32, 64, 0.4
+                layer = Q.Quantize(d, k, do_kmeans_init=False, codebook_normalize=normalize,
+                                   commitment_weight=beta, forward_mode=mode)
+                with torch.no_grad():
+                    layer.embedding.weight.copy_(torch.rand(k, d, generator=gen))
+                layer.train(training)
+                x = (unit_rows(n, d, gen) * (0.5 + torch.rand(n, 1, generator=gen))).requires_grad_(True)
+                g_emb = torch.randn(n, d, generator=gen)
+                g_loss = torch.randn(n, generator=gen)
+                res = layer(x, temperature=0.2)
+                ((res.embeddings * g_emb).sum() + (res.loss * g_loss).sum()).backward()
+                tag = f"{mname}_norm{int(normalize)}_train{int(training)}"
+                out.update({
+                    f"{tag}/x": _np(x), f"{tag}/weight": _np(layer.embedding.weight),
+                    f"{tag}/g_emb": _np(g_emb), f"{tag}/g_loss": _np(g_loss),
+                    f"{tag}/emb_out": _np(res.embeddings), f"{tag}/ids": _np(res.ids),
+                    f"{tag}/loss": _np(res.loss), f"{tag}/grad_x": _np(x.grad),
+                    f"{tag}/grad_weight": _np(layer.embedding.weight.grad),
+                    f"{tag}/beta": np.float32(beta),
+                })
+    # Gumbel-softmax with the uniform noise recorded (distributions/gumbel.py:8-18 draws torch.rand)
+    gen = torch.Generator().manual_seed(5)
+    n, d, k = 16, 32, 64
+    layer = Q.Quantize(d, k, do_kmeans_init=False, commitment_weight=0.25,
+                       forward_mode=Q.QuantizeForwardMode.GUMBEL_SOFTMAX)
+    with torch.no_grad():
+        layer.embedding.weight.copy_(torch.rand(k, d, generator=gen))
+    layer.train(True)
+    x = unit_rows(n, d, gen)
+    torch.manual_seed(123)
+    uniform = torch.rand((n, k))
+    torch.manual_seed(123)
+    res = layer(x, temperature=0.2)
+    out.update({"gumbel/x": _np(x), "gumbel/weight": _np(layer.embedding.weight), "gumbel/uniform": _np(uniform),
+                "gumbel/emb_out": _np(res.embeddings), "gumbel/ids": _np(res.ids), "gumbel/loss": _np(res.loss)})
+    np.savez_compressed(os.path.join(OUT, "quantize_levels.npz"), **out)
+
+
+def make_rq_cases(ref):
+    """`HRqVae.get_semantic_ids` without tags (modules/h_rqvae.py:481-583), C1 shape: D=32 K=256 L=3."""
+    Q = ref.quantize
+    H = ref.h_rqvae
+    modes = {"ste": Q.QuantizeForwardMode.STE, "rot": Q.QuantizeForwardMode.ROTATION_TRICK}
+    out = {}
+    for mname, mode in modes.items():
+        for training in (True, False):
+            gen = torch.Generator().manual_seed(3)
+            n, d, k, L, beta = 64, 32, 256, 3, 0.4
+            model = H.HRqVae(input_dim=48, embed_dim=d, hidden_dims=[40], codebook_size=k,
+                             codebook_kmeans_init=False, codebook_normalize=True, codebook_mode=mode,
+                             n_layers=L, commitment_weight=beta, n_cat_features=0,
+                             tag_class_counts=[5, 7, 9], tag_embed_dim=16)
+            with torch.no_grad():
+                for layer in model.layers:
+                    layer.embedding.weight.copy_(torch.rand(k, d, generator=gen))
+                # make later levels comparable in scale to the residuals so every level is exercised
+                model.layers[1].embedding.weight.mul_(0.25).sub_(0.125)
+                model.layers[2].embedding.weight.mul_(0.1).sub_(0.05)
+            model.train(training)
+            enc = unit_rows(n, d, gen).requires_grad_(True)
+            g_emb = torch.randn(n, d, L, generator=gen)
+            g_loss = torch.randn(n, generator=gen)
+            res = model.get_semantic_ids(enc)
+            ((res.embeddings * g_emb).sum() + (res.quantize_loss * g_loss).sum()).backward()
+            tag = f"{mname}_train{int(training)}"
+            out.update({
+                f"{tag}/enc": _np(enc), f"{tag}/g_emb": _np(g_emb), f"{tag}/g_loss": _np(g_loss),
+                f"{tag}/weights": np.stack([_np(l.embedding.weight) for l in model.layers]),
+                f"{tag}/embeddings": _np(res.embeddings), f"{tag}/residuals": _np(res.residuals),
+                f"{tag}/sem_ids": _np(res.sem_ids), f"{tag}/quantize_loss": _np(res.quantize_loss),
+                f"{tag}/grad_enc": _np(enc.grad),
+                f"{tag}/grad_weights": np.stack([_np(l.embedding.weight.grad) for l in model.layers]),
+                f"{tag}/beta": np.float32(beta),
+            })
+    np.savez_compressed(os.path.join(OUT, "rq_c1.npz"), **out)
+
+
+def make_uniqueness_cases(ref):
+    """`SemanticIdUniquenessLoss` (modules/h_rqvae.py:25-105) and p_unique_ids (:645-648)."""
+    H = ref.h_rqvae
+    from einops import rearrange
+    gen = torch.Generator().manual_seed(9)
+    out = {}
+    for name, (b, L, k, margin, weight) in {"dups": (96, 3, 3, 0.0, 1.5), "margin": (64, 3, 2, 0.5, 0.5),
+                                           "nodup": (40, 3, 256, 0.0, 1.5)}.items():
+        ids = torch.randint(0, k, (b, L), generator=gen)
+        if name == "nodup":
+            ids[:, 0] = torch.arange(b)
+        feats = torch.randn(b, 32, generator=gen).requires_grad_(True)
+        loss_fn = H.SemanticIdUniquenessLoss(margin=margin, weight=weight)
+        loss = loss_fn(ids, feats)
+        if loss.requires_grad:
+            loss.backward()
+            grad = _np(feats.grad)
+        else:
+            grad = np.zeros((b, 32), np.float32)
+        as_wired = loss_fn(ids.transpose(0, 1), feats.detach())  # what HRqVae.forward actually calls (:630-631)
+        p_unique = (~torch.triu((rearrange(ids, "b d -> b 1 d") == rearrange(ids, "b d -> 1 b d")).all(axis=-1),
+                                diagonal=1)).all(axis=1).sum() / ids.shape[0]
+        out.update({f"{name}/ids": _np(ids), f"{name}/feats": _np(feats), f"{name}/loss": _np(loss),
+                    f"{name}/grad_feats": grad, f"{name}/loss_as_wired": _np(as_wired),
+                    f"{name}/p_unique": _np(p_unique), f"{name}/margin": np.float32(margin),
+                    f"{name}/weight": np.float32(weight)})
+    np.savez_compressed(os.path.join(OUT, "uniqueness.npz"), **out)
+
+
+def make_kmeans_cases(ref):
+    """`Kmeans(k).run(x)` (init/kmeans.py:63-77) with the NumPy-global-RNG initial rows recorded."""
+    K = ref.kmeans
+    out = {}
+    for name, (n, d, k, seed) in {"blobs": (600, 8, 12, 4), "unit32": (2000, 32, 64, 7)}.items():
+        gen = torch.Generator().manual_seed(seed)
+        if name == "blobs":
+            centers = torch.randn(k, d, generator=gen) * 4
+            x = centers[torch.randint(0, k, (n,), generator=gen)] + 0.3 * torch.randn(n, d, generator=gen)
+        else:
+            x = unit_rows(n, d, gen)
+        np.random.seed(seed)
+        init_idx = np.random.choice(n, k, replace=False)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        import io, contextlib
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = K.Kmeans(k=k).run(x)
+        out.update({f"{name}/x": _np(x), f"{name}/init_idx": init_idx.astype(np.int64),
+                    f"{name}/centroids": _np(res.centroids), f"{name}/assignment": _np(res.assignment)})
+    np.savez_compressed(os.path.join(OUT, "kmeans.npz"), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)  # fixed reduction order for the recorded values
+    ref = load_reference()
+    make_quantize_cases(ref)
+    make_rq_cases(ref)
+    make_uniqueness_cases(ref)
+    make_kmeans_cases(ref)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
