@@ -1,0 +1,143 @@
+// Shared host/device helpers for the hidvae_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/hidvae_b200.h"
+
+namespace hv {
+
+// thread-local error text behind hv_last_error()
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define HV_CUDA_CHECK(expr)                                       \
+  do {                                                            \
+    cudaError_t _e = (expr);                                      \
+    if (_e != cudaSuccess) return ::hv::cuda_fail(_e, #expr);     \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct DeviceProps {
+  int sm_count = 0;
+  int cc_major = 0;
+  int cc_minor = 0;
+  int max_smem_optin = 0;
+};
+// cached per device; returns non-zero status on failure
+int device_props(DeviceProps* out);
+
+// Arguments of the fused forward, shared by the SIMT and tcgen05 variants.
+struct RqFwdArgs {
+  const float* x;
+  const float* codebooks;  // [L, K, D] fp32, effective
+  int64_t n;
+  int n_levels;
+  int k;
+  float beta;
+  int64_t* ids;
+  int64_t ids_row_stride;
+  int64_t ids_level_stride;
+  float* emb_out;         // [L, N, D] or null
+  float* residuals;       // [L, N, D] or null
+  float* loss;            // [N] or null
+  float* level_loss;      // [L, N] or null
+  float* final_residual;  // [N, D] or null
+};
+
+int launch_rq_fwd_simt(const RqFwdArgs& a, int d, bool rot, bool diff_form, cudaStream_t stream);
+// returns HV_ERR_UNSUPPORTED when the shape has no tcgen05 instantiation
+int launch_rq_fwd_tc(const RqFwdArgs& a, int d, bool rot, void* workspace, size_t workspace_bytes, bool prepacked,
+                     cudaStream_t stream);
+int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream);
+bool rq_fwd_tc_supported(int d, int k, int n_levels);
+size_t rq_fwd_tc_workspace_bytes(int d, int k, int n_levels);
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-row "tail" of one quantiser level: everything after the argmin.  One thread owns one row in registers.
+//   r      in : residual entering the level (r_l)            out: r_{l+1} = r_l - o_l
+//   e         : the chosen code row C_l[id] (fp32)
+//   returns the level loss a + beta*a with a = |r - e|^2      (modules/loss.py:41-44)
+//   o (emb_out) is written to `o_out` when non-null.
+// ROT implements modules/quantize.py:34-45,134-140 literally:  o = r - 2 (r.w) w + 2 (r.u) q
+// ---------------------------------------------------------------------------------------------------------
+template <int D, bool ROT>
+__device__ __forceinline__ float rq_level_tail(float (&r)[D], const float (&e)[D], float beta, float* o_out) {
+  float a = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const float df = r[i] - e[i];
+    a = fmaf(df, df, a);
+  }
+  const float level_loss = a + beta * a;
+  if constexpr (!ROT) {
+    if (o_out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < D; i += 4)
+        *reinterpret_cast<float4*>(o_out + i) = make_float4(e[i], e[i + 1], e[i + 2], e[i + 3]);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) r[i] = r[i] - e[i];
+  } else {
+    float rr = 0.f, ee = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      rr = fmaf(r[i], r[i], rr);
+      ee = fmaf(e[i], e[i], ee);
+    }
+    const float inv_r = 1.0f / (sqrtf(rr) + 1e-8f);  // u = r / (|r| + 1e-8)
+    const float inv_e = 1.0f / (sqrtf(ee) + 1e-8f);  // q = e / (|e| + 1e-8)
+    float ss = 0.f, ru = 0.f, rs = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const float u = r[i] * inv_r;
+      const float q = e[i] * inv_e;
+      const float s = u + q;
+      ss = fmaf(s, s, ss);
+      ru = fmaf(r[i], u, ru);
+      rs = fmaf(r[i], s, rs);
+    }
+    const float inv_s = 1.0f / fmaxf(sqrtf(ss), 1e-6f);  // w = (u+q) / max(|u+q|, 1e-6)
+    const float rw2 = 2.0f * (rs * inv_s);               // 2 (r.w)
+    const float ru2 = 2.0f * ru;                         // 2 (r.u)
+    float o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const float u = r[i] * inv_r;
+      const float q = e[i] * inv_e;
+      const float w = (u + q) * inv_s;
+      o[i] = r[i] - rw2 * w + ru2 * q;
+    }
+    if (o_out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < D; i += 4)
+        *reinterpret_cast<float4*>(o_out + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) r[i] = r[i] - o[i];
+  }
+  return level_loss;
+}
+
+template <int D>
+__device__ __forceinline__ void load_row(float (&dst)[D], const float* __restrict__ src) {
+#pragma unroll
+  for (int i = 0; i < D; i += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+    dst[i] = v.x, dst[i + 1] = v.y, dst[i + 2] = v.z, dst[i + 3] = v.w;
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void store_row(float* __restrict__ dst, const float (&src)[D]) {
+#pragma unroll
+  for (int i = 0; i < D; i += 4)
+    *reinterpret_cast<float4*>(dst + i) = make_float4(src[i], src[i + 1], src[i + 2], src[i + 3]);
+}
+
+}  // namespace hv

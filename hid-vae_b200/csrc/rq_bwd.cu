@@ -1,0 +1,242 @@
+// Fused backward of the L-level residual quantiser (STE / rotation trick / eval) -- HBM-bound, no GEMM.
+//
+// One pass over the rows.  A row is spread over D/4 lanes (one float4 each) so every global access of a warp
+// is a run of contiguous 16-byte pieces; dot products are reduced with xor-shuffles inside the lane group.
+// The forward chain r_l, e_l is recomputed from x, ids and the codebooks (nothing was saved by the forward),
+// then the recursion of SURVEY.md section 8a runs from the last level to the first:
+//     h   = g_emb_l - G                      (G = dLoss/d r_{l+1})
+//     Jh  = h                                (STE)      | h - 2 (h.w) w + 2 (h.q) u   (rotation trick)
+//     G   = G + Jh + 2 beta (r_l - e_l) g_loss          | eval: G = G + 2 beta (r_l - e_l) g_loss
+//     gC_l[id_l] += 2 (e_l - r_l) g_loss                | eval: += h + 2 (e_l - r_l) g_loss
+// The codebook gradient is a scatter-add by id (the embedding_dense_backward of modules/quantize.py:97-98):
+// when [L, K, D] fits, it is accumulated with shared-memory atomics per CTA and flushed once, otherwise (or for
+// small N) with global red.add.
+#include "common.cuh"
+
+namespace hv {
+namespace {
+
+constexpr int kMaxLevels = 8;
+constexpr int kBwdThreads = 256;
+
+struct RqBwdArgs {
+  const float* x;
+  const float* codebooks;
+  int64_t n;
+  int n_levels;
+  int k;
+  float beta;
+  int training;
+  const int64_t* ids;
+  int64_t ids_row_stride;
+  int64_t ids_level_stride;
+  const float* g_emb;
+  int64_t g_emb_level_stride;
+  int64_t g_emb_row_stride;
+  const float* g_loss;
+  int64_t g_loss_stride;
+  const float* g_level_loss;
+  float* g_x;
+  float* g_codebooks;
+};
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+template <int D, bool ROT, bool SMEM_ACC>
+__global__ void __launch_bounds__(kBwdThreads) rq_bwd_kernel(RqBwdArgs a) {
+  constexpr int LPR = D / 4;  // lanes per row
+  constexpr int ROWS_PER_WARP = 32 / LPR;
+  extern __shared__ __align__(16) float s_gc[];  // [L, K, D] when SMEM_ACC
+
+  const int64_t lkd = static_cast<int64_t>(a.n_levels) * a.k * D;
+  if (SMEM_ACC) {
+    for (int64_t i = threadIdx.x; i < lkd; i += kBwdThreads) s_gc[i] = 0.f;
+    __syncthreads();
+  }
+
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int warp_global = (blockIdx.x * kBwdThreads + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * kBwdThreads) >> 5;
+  const int64_t n_groups = (a.n + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
+  const bool rot = ROT && a.training;
+
+  for (int64_t g = warp_global; g < n_groups; g += n_warps) {
+    const int64_t row = g * ROWS_PER_WARP + lane / LPR;
+    const bool valid = row < a.n;
+    const int64_t rrow = valid ? row : 0;  // keep every lane in the shuffles; mask the stores
+
+    float4 R[kMaxLevels], E[kMaxLevels];
+    float inv_r[kMaxLevels], inv_e[kMaxLevels], inv_s[kMaxLevels];
+    int64_t id[kMaxLevels];
+    float4 r = __ldg(reinterpret_cast<const float4*>(a.x + rrow * D) + sub);
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) {
+      if (l < a.n_levels) {
+        int64_t code = a.ids[rrow * a.ids_row_stride + l * a.ids_level_stride];
+        code = code < 0 ? 0 : (code >= a.k ? a.k - 1 : code);
+        id[l] = code;
+        const float4 e = __ldg(reinterpret_cast<const float4*>(a.codebooks + (static_cast<int64_t>(l) * a.k + code) * D) + sub);
+        R[l] = r;
+        E[l] = e;
+        float4 o = e;
+        if (rot) {
+          const float rr = group_sum<LPR>(dot4(r, r));
+          const float ee = group_sum<LPR>(dot4(e, e));
+          const float ir = 1.0f / (sqrtf(rr) + 1e-8f);
+          const float ie = 1.0f / (sqrtf(ee) + 1e-8f);
+          const float4 u = make_float4(r.x * ir, r.y * ir, r.z * ir, r.w * ir);
+          const float4 q = make_float4(e.x * ie, e.y * ie, e.z * ie, e.w * ie);
+          const float4 s = make_float4(u.x + q.x, u.y + q.y, u.z + q.z, u.w + q.w);
+          const float ss = group_sum<LPR>(dot4(s, s));
+          const float ru = group_sum<LPR>(dot4(r, u));
+          const float rs = group_sum<LPR>(dot4(r, s));
+          const float is = 1.0f / fmaxf(sqrtf(ss), 1e-6f);
+          inv_r[l] = ir, inv_e[l] = ie, inv_s[l] = is;
+          const float rw2 = 2.0f * (rs * is), ru2 = 2.0f * ru;
+          o.x = r.x - rw2 * (s.x * is) + ru2 * q.x;
+          o.y = r.y - rw2 * (s.y * is) + ru2 * q.y;
+          o.z = r.z - rw2 * (s.z * is) + ru2 * q.z;
+          o.w = r.w - rw2 * (s.w * is) + ru2 * q.w;
+        }
+        r = make_float4(r.x - o.x, r.y - o.y, r.z - o.z, r.w - o.w);
+      }
+    }
+
+    const float gl_all = a.g_loss != nullptr ? a.g_loss[rrow * a.g_loss_stride] : 0.f;
+    float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = kMaxLevels - 1; l >= 0; --l) {
+      if (l < a.n_levels) {
+        float gl = gl_all;
+        if (a.g_level_loss != nullptr) gl += a.g_level_loss[static_cast<int64_t>(l) * a.n + rrow];
+        float4 h = make_float4(-G.x, -G.y, -G.z, -G.w);
+        if (a.g_emb != nullptr) {
+          const float4 ge = __ldg(reinterpret_cast<const float4*>(a.g_emb + l * a.g_emb_level_stride + rrow * a.g_emb_row_stride) + sub);
+          h.x += ge.x, h.y += ge.y, h.z += ge.z, h.w += ge.w;
+        }
+        const float4 rl = R[l], el = E[l];
+        const float4 diff = make_float4(rl.x - el.x, rl.y - el.y, rl.z - el.z, rl.w - el.w);
+        const float c2 = 2.0f * gl;
+        float4 ge_code = make_float4(-c2 * diff.x, -c2 * diff.y, -c2 * diff.z, -c2 * diff.w);
+        const float cb2 = a.beta * c2;
+        if (a.training) {
+          float4 jh = h;
+          if (rot) {
+            const float ir = inv_r[l], ie = inv_e[l], is = inv_s[l];
+            const float4 u = make_float4(rl.x * ir, rl.y * ir, rl.z * ir, rl.w * ir);
+            const float4 q = make_float4(el.x * ie, el.y * ie, el.z * ie, el.w * ie);
+            const float4 w = make_float4((u.x + q.x) * is, (u.y + q.y) * is, (u.z + q.z) * is, (u.w + q.w) * is);
+            const float hw2 = 2.0f * group_sum<LPR>(dot4(h, w));
+            const float hq2 = 2.0f * group_sum<LPR>(dot4(h, q));
+            jh.x = h.x - hw2 * w.x + hq2 * u.x;
+            jh.y = h.y - hw2 * w.y + hq2 * u.y;
+            jh.z = h.z - hw2 * w.z + hq2 * u.z;
+            jh.w = h.w - hw2 * w.w + hq2 * u.w;
+          }
+          G.x += jh.x + cb2 * diff.x, G.y += jh.y + cb2 * diff.y;
+          G.z += jh.z + cb2 * diff.z, G.w += jh.w + cb2 * diff.w;
+        } else {
+          G.x += cb2 * diff.x, G.y += cb2 * diff.y, G.z += cb2 * diff.z, G.w += cb2 * diff.w;
+          ge_code.x += h.x, ge_code.y += h.y, ge_code.z += h.z, ge_code.w += h.w;
+        }
+        if (valid) {
+          const int64_t off = (static_cast<int64_t>(l) * a.k + id[l]) * D + sub * 4;
+          float* dst = SMEM_ACC ? s_gc + off : a.g_codebooks + off;
+          atomicAdd(dst + 0, ge_code.x);
+          atomicAdd(dst + 1, ge_code.y);
+          atomicAdd(dst + 2, ge_code.z);
+          atomicAdd(dst + 3, ge_code.w);
+        }
+      }
+    }
+    if (valid) reinterpret_cast<float4*>(a.g_x + row * D)[sub] = G;
+  }
+
+  if (SMEM_ACC) {
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < lkd; i += kBwdThreads) {
+      const float v = s_gc[i];
+      if (v != 0.f) atomicAdd(a.g_codebooks + i, v);
+    }
+  }
+}
+
+template <int D>
+int launch_d(const RqBwdArgs& a, bool rot, cudaStream_t stream) {
+  DeviceProps props;
+  if (int st = device_props(&props)) return st;
+  constexpr int LPR = D / 4;
+  constexpr int rows_per_cta = (kBwdThreads / 32) * (32 / LPR);
+  const size_t acc_bytes = static_cast<size_t>(a.n_levels) * a.k * D * sizeof(float);
+  // shared-memory accumulation pays off once every CTA sees clearly more rows than it has accumulators to flush
+  const bool smem_acc = acc_bytes <= 100 * 1024 && a.n >= static_cast<int64_t>(props.sm_count) * a.k * 4;
+  int64_t ctas = (a.n + rows_per_cta - 1) / rows_per_cta;
+  const int64_t cap = static_cast<int64_t>(props.sm_count) * (smem_acc ? 2 : 8);
+  if (ctas > cap) ctas = cap;
+  auto go = [&](auto kernel, size_t smem) -> int {
+    if (smem > 48 * 1024) HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<static_cast<unsigned>(ctas), kBwdThreads, smem, stream>>>(a);
+    HV_CUDA_CHECK(cudaGetLastError());
+    return HV_OK;
+  };
+  if (smem_acc) return rot ? go(rq_bwd_kernel<D, true, true>, acc_bytes) : go(rq_bwd_kernel<D, false, true>, acc_bytes);
+  return rot ? go(rq_bwd_kernel<D, true, false>, 0) : go(rq_bwd_kernel<D, false, false>, 0);
+}
+
+}  // namespace
+}  // namespace hv
+
+extern "C" int hv_rq_backward(const float* x, int64_t n, int d, const float* codebooks, int n_levels, int k, int mode,
+                              int training, float beta, const int64_t* ids, int64_t ids_row_stride,
+                              int64_t ids_level_stride, const float* g_emb, int64_t g_emb_level_stride,
+                              int64_t g_emb_row_stride, const float* g_loss, int64_t g_loss_stride,
+                              const float* g_level_loss, float* g_x, float* g_codebooks, void* stream) {
+  using namespace hv;
+  if (n < 0 || d <= 0 || k <= 0 || n_levels <= 0) {
+    set_error("hv_rq_backward: bad shape n=%lld d=%d k=%d L=%d", (long long)n, d, k, n_levels);
+    return HV_ERR_BAD_SHAPE;
+  }
+  if (n_levels > kMaxLevels) {
+    set_error("hv_rq_backward: at most %d levels are supported (got %d)", kMaxLevels, n_levels);
+    return HV_ERR_UNSUPPORTED;
+  }
+  if (mode != HV_MODE_STE && mode != HV_MODE_ROTATION_TRICK) {
+    set_error("hv_rq_backward: forward mode %d has no fused kernel (STE=2, ROTATION_TRICK=3)", mode);
+    return HV_ERR_UNSUPPORTED;
+  }
+  if (n == 0) return HV_OK;
+  if (!x || !codebooks || !ids || !g_x || !g_codebooks) {
+    set_error("hv_rq_backward: null pointer");
+    return HV_ERR_NULL;
+  }
+  if (!aligned16(x) || !aligned16(codebooks) || !aligned16(g_x) || (g_emb && !aligned16(g_emb)) ||
+      (g_emb && ((g_emb_level_stride % 4) || (g_emb_row_stride % 4)))) {
+    set_error("hv_rq_backward: x, codebooks, g_x, g_emb must be 16-byte aligned with strides that are multiples of 4");
+    return HV_ERR_MISALIGNED;
+  }
+  RqBwdArgs a{x, codebooks, n, n_levels, k, beta, training ? 1 : 0, ids, ids_row_stride, ids_level_stride,
+              g_emb, g_emb_level_stride, g_emb_row_stride, g_loss, g_loss_stride, g_level_loss, g_x, g_codebooks};
+  const bool rot = mode == HV_MODE_ROTATION_TRICK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (d) {
+    case 4: return launch_d<4>(a, rot, s);
+    case 8: return launch_d<8>(a, rot, s);
+    case 16: return launch_d<16>(a, rot, s);
+    case 32: return launch_d<32>(a, rot, s);
+    case 64: return launch_d<64>(a, rot, s);
+    case 128: return launch_d<128>(a, rot, s);
+    default:
+      set_error("hv_rq_backward: embed dim %d has no instantiation (supported: 4, 8, 16, 32, 64, 128)", d);
+      return HV_ERR_UNSUPPORTED;
+  }
+}

@@ -1,0 +1,484 @@
+// tcgen05 variant of the fused L-level residual quantiser (HV_ALGO_TCGEN05) for sm_100a.
+//
+// Mapping (re-derived for B200):
+//   GEMM  M = 128 rows of one row tile (= the 128 TMEM lanes), N = up to 256 codes, reduction = D.
+//   score[row, k] = r.c_k - |c_k|^2 / 2   (argmax == argmin of |r|^2 + |c_k|^2 - 2 r.c_k; |r|^2 is row-constant)
+//   fp32-grade scores from bf16 tensor cores: r = r_hi + r_lo, c = c_hi + c_lo (bf16 each), three products
+//   r_hi.c_hi + r_lo.c_hi + r_hi.c_lo accumulated in the fp32 TMEM accumulator, and -|c|^2/2 folded in as one
+//   more K=16 step (A = [1,1,1,0..], B = the norm split in three bf16 pieces).  3*D/16 + 1 tcgen05.mma per tile.
+//   The codebooks are pre-packed once per launch into the UMMA K-major core-matrix layout and staged by 1-D
+//   bulk TMA copies: resident in shared memory for all L levels when they fit (K=256, D=32, L=3: 120 KB),
+//   otherwise streamed through a ring of stages (K=4096, D=64).
+//   One CTA (persistent, one per SM) works on two row tiles at once: two epilogue warpgroups, each owning one
+//   256-column fp32 accumulator (2 x 256 = all 512 TMEM columns), so the MMAs of one tile overlap the argmin
+//   epilogue of the other.  Warp 8 is the TMA producer, warp 9 allocates TMEM and issues every tcgen05.mma.
+//   Epilogue thread t owns row t of its tile for all L levels: tcgen05.ld (32x32b) hands it whole rows, the
+//   running (max, argmax) stays in registers, then it gathers the fp32 code row, forms emb_out / loss / the next
+//   residual in registers and re-stages the residual (bf16 hi/lo) as the next level's A operand.
+//   The [N, K] score matrix never leaves the SM.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace hv {
+namespace {
+
+constexpr int kTileRows = 128;
+constexpr int kEpiWarps = 8;
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kThreads = 320;
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = 256;
+constexpr int kMaxStages = 16;
+constexpr int kOnesBytes = 2 * kTileRows * 16;  // one K=16 step of the A operand: [2 chunks][128 rows][8 bf16]
+constexpr int kSmemLimit = 227 * 1024;
+
+struct TcPlan {
+  int ntile;       // codes per N tile (multiple of 32, <= 256)
+  int n_ktiles;    // N tiles per level
+  int tile_bytes;  // packed image of one (level, N tile)
+  int stages;      // shared-memory stages for packed images
+  int resident;    // 1: every (level, tile) image has its own stage and is loaded once
+  int smem_bytes;
+  int a_bytes;     // one warpgroup's A operand (hi + lo)
+};
+
+bool make_plan(int d, int k, int n_levels, TcPlan* p) {
+  if (d % 16 != 0 || d < 16 || d > 128 || k < 1 || n_levels < 1) return false;
+  const int kpad = (k + 31) / 32 * 32;
+  p->ntile = kpad <= 256 ? kpad : 256;
+  p->n_ktiles = (k + p->ntile - 1) / p->ntile;
+  p->tile_bytes = p->ntile * (4 * d + 32);
+  p->a_bytes = kTileRows * d * 4;
+  const int fixed = 2 * p->a_bytes + kOnesBytes + 1024;
+  const int budget = kSmemLimit - fixed;
+  const int total_tiles = n_levels * p->n_ktiles;
+  if (total_tiles <= kMaxStages && static_cast<long long>(total_tiles) * p->tile_bytes <= budget) {
+    p->resident = 1;
+    p->stages = total_tiles;
+  } else {
+    p->resident = 0;
+    p->stages = budget / p->tile_bytes;
+    if (p->stages > 4) p->stages = 4;
+    if (p->stages < 2) return false;
+  }
+  p->smem_bytes = fixed + p->stages * p->tile_bytes;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pack kernel: fp32 [L, K, D] -> per (level, N tile) image
+//   [c_hi : D/8 chunks][c_lo : D/8 chunks][norm : 2 chunks], chunk = [ntile codes][8 bf16] (16 B per code)
+// Padded codes (index >= K) get zero vectors and a -1e30 norm term so they can never win the argmax.
+// ---------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void rq_pack_codebooks_kernel(const float* __restrict__ codebooks, int n_levels, int k, int ntile,
+                                         int n_ktiles, int tile_bytes, uint8_t* __restrict__ packed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (level, tile, code in tile)
+  const int total = n_levels * n_ktiles * ntile;
+  if (idx >= total) return;
+  const int c = idx % ntile;
+  const int tile = idx / ntile;  // level * n_ktiles + t
+  const int t = tile % n_ktiles;
+  const int level = tile / n_ktiles;
+  const int code = t * ntile + c;
+  uint8_t* img = packed + static_cast<size_t>(tile) * tile_bytes;
+  const size_t chunk_stride = static_cast<size_t>(ntile) * 16;
+  uint8_t* hi_base = img;
+  uint8_t* lo_base = img + (D / 8) * chunk_stride;
+  uint8_t* nrm_base = img + 2 * (D / 8) * chunk_stride;
+
+  float v[D];
+  const bool real = code < k;
+  if (real) {
+    load_row<D>(v, codebooks + (static_cast<int64_t>(level) * k + code) * D);
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = 0.f;
+  }
+  float cc = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) cc = fmaf(v[i], v[i], cc);
+#pragma unroll
+  for (int kc = 0; kc < D / 8; ++kc) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x0 = v[kc * 8 + 2 * j], x1 = v[kc * 8 + 2 * j + 1];
+      const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - __low2float(h), x1 - __high2float(h));
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    *reinterpret_cast<uint4*>(hi_base + kc * chunk_stride + c * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(lo_base + kc * chunk_stride + c * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  const float nv = real ? -0.5f * cc : -1e30f;
+  const __nv_bfloat16 n1 = __float2bfloat16_rn(nv);
+  const float rem1 = nv - __bfloat162float(n1);
+  const __nv_bfloat16 n2 = __float2bfloat16_rn(rem1);
+  const __nv_bfloat16 n3 = __float2bfloat16_rn(rem1 - __bfloat162float(n2));
+  const uint32_t w0 = static_cast<uint32_t>(__bfloat16_as_ushort(n1)) | (static_cast<uint32_t>(__bfloat16_as_ushort(n2)) << 16);
+  const uint32_t w1 = static_cast<uint32_t>(__bfloat16_as_ushort(n3));
+  *reinterpret_cast<uint4*>(nrm_base + c * 16) = make_uint4(w0, w1, 0u, 0u);
+  *reinterpret_cast<uint4*>(nrm_base + chunk_stride + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+struct TcParams {
+  const uint8_t* packed;
+  int ntile;
+  int n_ktiles;
+  int tile_bytes;
+  int stages;
+  int resident;
+  int a_bytes;
+};
+
+// bf16 hi/lo split of one row into the K-major core-matrix layout: chunk kc of row `row` lives at
+// base + kc * (128 rows * 16 B) + row * 16.
+template <int D>
+__device__ __forceinline__ void stage_a_operand(uint8_t* a_hi, uint8_t* a_lo, int row, const float (&r)[D]) {
+#pragma unroll
+  for (int kc = 0; kc < D / 8; ++kc) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x0 = r[kc * 8 + 2 * j], x1 = r[kc * 8 + 2 * j + 1];
+      const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - __low2float(h), x1 - __high2float(h));
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    *reinterpret_cast<uint4*>(a_hi + kc * (kTileRows * 16) + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(a_lo + kc * (kTileRows * 16) + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int base, float& best, int& best_k) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float s = __uint_as_float(v[j]);
+    if (s > best) {  // strict: the first (lowest) index wins exact ties, like torch.min on the distances
+      best = s;
+      best_k = base + j;
+    }
+  }
+}
+
+template <int D, bool ROT>
+__global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // [A wg0 hi | A wg0 lo | A wg1 hi | A wg1 lo | ones | barriers (1 KB) | B stages ...]
+  uint8_t* s_a = smem;
+  uint8_t* s_ones = smem + 2 * p.a_bytes;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ones + kOnesBytes);
+  uint8_t* s_b = s_ones + kOnesBytes + 1024;
+
+  uint64_t* bar_b_full = s_bar;                     // [kMaxStages]
+  uint64_t* bar_b_empty = s_bar + kMaxStages;       // [kMaxStages]
+  uint64_t* bar_a_ready = s_bar + 2 * kMaxStages;   // [2]
+  uint64_t* bar_acc_full = bar_a_ready + 2;         // [2]
+  uint64_t* bar_acc_empty = bar_acc_full + 2;       // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == kProducerWarp && lane == 0) {
+    for (int s = 0; s < kMaxStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bar_b_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bar_b_empty[s]), 1);
+    }
+    for (int w = 0; w < 2; ++w) {
+      ptx::mbar_init(ptx::smem_u32(&bar_a_ready[w]), 4);
+      ptx::mbar_init(ptx::smem_u32(&bar_acc_full[w]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bar_acc_empty[w]), 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    ptx::tmem_alloc(ptx::smem_u32(s_tmem), kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  if (threadIdx.x < kTileRows) {
+    // constant A block that multiplies the norm pieces: row -> [1, 1, 1, 0, 0, 0, 0, 0 | 0 x 8]
+    const uint32_t one2 = 0x3F803F80u;  // bf16 (1.0, 1.0)
+    *reinterpret_cast<uint4*>(s_ones + threadIdx.x * 16) = make_uint4(one2, 0x00003F80u, 0u, 0u);
+    *reinterpret_cast<uint4*>(s_ones + kTileRows * 16 + threadIdx.x * 16) = make_uint4(0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async_smem();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
+  const int64_t n_pairs = (n_row_tiles + 1) / 2;
+  const int total_tiles = a.n_levels * p.n_ktiles;
+
+  if (warp < kEpiWarps) {
+    // ===================================== epilogue warpgroups ============================================
+    const int w = warp >> 2;                       // warpgroup = which row tile of the pair / which accumulator
+    const int row_in_tile = threadIdx.x - w * kTileRows;
+    const int quarter = warp & 3;                  // TMEM lanes [32*quarter, 32*quarter + 32)
+    uint8_t* a_hi = s_a + w * p.a_bytes;
+    uint8_t* a_lo = a_hi + p.a_bytes / 2;
+    const uint32_t acc_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + w * kAccCols;
+    const uint32_t bar_ready = ptx::smem_u32(&bar_a_ready[w]);
+    const uint32_t bar_full = ptx::smem_u32(&bar_acc_full[w]);
+    const uint32_t bar_empty = ptx::smem_u32(&bar_acc_empty[w]);
+    const int n_chunks = p.ntile / 32;
+    uint32_t acc_phase = 0;
+
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int64_t row = (2 * pair + w) * kTileRows + row_in_tile;
+      const bool valid = row < a.n;
+      float r[D];
+      if (valid) {
+        load_row<D>(r, a.x + row * D);
+      } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) r[i] = 0.f;
+      }
+      float total_loss = 0.f;
+      for (int l = 0; l < a.n_levels; ++l) {
+        if (valid && a.residuals != nullptr) store_row<D>(a.residuals + (static_cast<int64_t>(l) * a.n + row) * D, r);
+        stage_a_operand<D>(a_hi, a_lo, row_in_tile, r);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_ready);
+
+        float best = -INFINITY;
+        int best_k = 0;
+        for (int t = 0; t < p.n_ktiles; ++t) {
+          ptx::mbar_wait(bar_full, acc_phase);
+          acc_phase ^= 1;
+          ptx::tc_fence_after_sync();
+          const int col0 = t * p.ntile;
+          uint32_t v0[32], v1[32];
+          ptx::tmem_ld_32x32(acc_addr, v0);
+          for (int c = 0; c < n_chunks; c += 2) {
+            ptx::tmem_wait_ld(v0);
+            if (c + 1 < n_chunks) ptx::tmem_ld_32x32(acc_addr + (c + 1) * 32, v1);
+            scan_chunk(v0, col0 + c * 32, best, best_k);
+            if (c + 1 < n_chunks) {
+              ptx::tmem_wait_ld(v1);
+              if (c + 2 < n_chunks) ptx::tmem_ld_32x32(acc_addr + (c + 2) * 32, v0);
+              scan_chunk(v1, col0 + (c + 1) * 32, best, best_k);
+            }
+          }
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_empty);
+        }
+        best_k = min(best_k, a.k - 1);
+
+        const float* cb = a.codebooks + static_cast<int64_t>(l) * a.k * D;
+        float e[D];
+        load_row<D>(e, cb + static_cast<int64_t>(best_k) * D);
+        float* o_out = (valid && a.emb_out != nullptr) ? a.emb_out + (static_cast<int64_t>(l) * a.n + row) * D : nullptr;
+        const float ll = rq_level_tail<D, ROT>(r, e, a.beta, o_out);
+        total_loss += ll;
+        if (valid) {
+          a.ids[row * a.ids_row_stride + l * a.ids_level_stride] = best_k;
+          if (a.level_loss != nullptr) a.level_loss[static_cast<int64_t>(l) * a.n + row] = ll;
+        }
+      }
+      if (valid) {
+        if (a.loss != nullptr) a.loss[row] = total_loss;
+        if (a.final_residual != nullptr) store_row<D>(a.final_residual + row * D, r);
+      }
+    }
+  } else if (warp == kProducerWarp) {
+    // ===================================== TMA producer ===================================================
+    if (lane == 0) {
+      if (p.resident) {
+        if (static_cast<int64_t>(blockIdx.x) < n_pairs) {
+          for (int s = 0; s < total_tiles; ++s) {
+            const uint32_t bar = ptx::smem_u32(&bar_b_full[s]);
+            ptx::mbar_arrive_expect_tx(bar, p.tile_bytes);
+            ptx::bulk_g2s(ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes),
+                          p.packed + static_cast<size_t>(s) * p.tile_bytes, p.tile_bytes, bar);
+          }
+        }
+      } else {
+        uint32_t it = 0;
+        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+          for (int tile = 0; tile < total_tiles; ++tile, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            ptx::mbar_wait(ptx::smem_u32(&bar_b_empty[s]), ph ^ 1);
+            const uint32_t bar = ptx::smem_u32(&bar_b_full[s]);
+            ptx::mbar_arrive_expect_tx(bar, p.tile_bytes);
+            ptx::bulk_g2s(ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes),
+                          p.packed + static_cast<size_t>(tile) * p.tile_bytes, p.tile_bytes, bar);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================== MMA issuer =====================================================
+    const uint32_t idesc = ptx::umma_idesc_bf16(kTileRows, p.ntile);
+    const uint32_t chunk_b = p.ntile * 16;        // bytes between K chunks of the B image
+    const uint32_t chunk_a = kTileRows * 16;      // bytes between K chunks of the A operand
+    uint32_t it = 0;
+    uint32_t a_phase[2] = {0, 0};
+    uint32_t acc_uses[2] = {0, 0};
+    bool first_pair = true;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (int tile = 0; tile < total_tiles; ++tile, ++it) {
+        const int t = tile % p.n_ktiles;
+        int s;
+        if (p.resident) {
+          s = tile;
+          if (first_pair) ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), 0);
+        } else {
+          s = it % p.stages;
+          ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), (it / p.stages) & 1);
+        }
+        const uint32_t b_hi = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
+        const uint32_t b_lo = b_hi + (D / 8) * chunk_b;
+        const uint32_t b_nrm = b_lo + (D / 8) * chunk_b;
+        for (int w = 0; w < 2; ++w) {
+          if (t == 0) {
+            ptx::mbar_wait(ptx::smem_u32(&bar_a_ready[w]), a_phase[w]);
+            a_phase[w] ^= 1;
+          }
+          ptx::mbar_wait(ptx::smem_u32(&bar_acc_empty[w]), (acc_uses[w] & 1) ^ 1);
+          acc_uses[w]++;
+          ptx::tc_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t acc = tmem_base + w * kAccCols;
+            const uint32_t a_hi = ptx::smem_u32(s_a + w * p.a_bytes);
+            const uint32_t a_lo = a_hi + p.a_bytes / 2;
+            uint32_t accumulate = 0;
+#pragma unroll
+            for (int j = 0; j < D / 16; ++j) {  // r_hi . c_hi
+              ptx::umma_bf16(acc, ptx::umma_smem_desc(a_hi + j * 2 * chunk_a, chunk_a, 128),
+                             ptx::umma_smem_desc(b_hi + j * 2 * chunk_b, chunk_b, 128), idesc, accumulate);
+              accumulate = 1;
+            }
+#pragma unroll
+            for (int j = 0; j < D / 16; ++j)  // r_lo . c_hi
+              ptx::umma_bf16(acc, ptx::umma_smem_desc(a_lo + j * 2 * chunk_a, chunk_a, 128),
+                             ptx::umma_smem_desc(b_hi + j * 2 * chunk_b, chunk_b, 128), idesc, 1);
+#pragma unroll
+            for (int j = 0; j < D / 16; ++j)  // r_hi . c_lo
+              ptx::umma_bf16(acc, ptx::umma_smem_desc(a_hi + j * 2 * chunk_a, chunk_a, 128),
+                             ptx::umma_smem_desc(b_lo + j * 2 * chunk_b, chunk_b, 128), idesc, 1);
+            // 1 * (-|c|^2 / 2)
+            ptx::umma_bf16(acc, ptx::umma_smem_desc(ptx::smem_u32(s_ones), chunk_a, 128),
+                           ptx::umma_smem_desc(b_nrm, chunk_b, 128), idesc, 1);
+            ptx::umma_commit(ptx::smem_u32(&bar_acc_full[w]));
+          }
+          __syncwarp();
+        }
+        if (!p.resident && lane == 0) ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
+        __syncwarp();
+      }
+      first_pair = false;
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int D>
+int pack_d(const float* codebooks, int n_levels, int k, const TcPlan& plan, uint8_t* packed, cudaStream_t stream) {
+  const int total_codes = n_levels * plan.n_ktiles * plan.ntile;
+  rq_pack_codebooks_kernel<D><<<(total_codes + 127) / 128, 128, 0, stream>>>(codebooks, n_levels, k, plan.ntile,
+                                                                           plan.n_ktiles, plan.tile_bytes, packed);
+  HV_CUDA_CHECK(cudaGetLastError());
+  return HV_OK;
+}
+
+template <int D>
+int launch_d(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, bool prepacked, cudaStream_t stream) {
+  if (!prepacked)
+    if (int st = pack_d<D>(a.codebooks, a.n_levels, a.k, plan, packed, stream)) return st;
+
+  DeviceProps props;
+  if (int st = device_props(&props)) return st;
+  const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
+  const int64_t n_pairs = (n_row_tiles + 1) / 2;
+  const unsigned grid = static_cast<unsigned>(n_pairs < props.sm_count ? n_pairs : props.sm_count);
+  TcParams p{packed, plan.ntile, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes};
+  auto go = [&](auto kernel) -> int {
+    HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    kernel<<<grid, kThreads, plan.smem_bytes, stream>>>(a, p);
+    HV_CUDA_CHECK(cudaGetLastError());
+    return HV_OK;
+  };
+  return rot ? go(rq_fwd_tc_kernel<D, true>) : go(rq_fwd_tc_kernel<D, false>);
+}
+
+}  // namespace
+
+bool rq_fwd_tc_supported(int d, int k, int n_levels) {
+  TcPlan plan;
+  return (d == 16 || d == 32 || d == 64) && make_plan(d, k, n_levels, &plan);
+}
+
+size_t rq_fwd_tc_workspace_bytes(int d, int k, int n_levels) {
+  TcPlan plan;
+  if (!rq_fwd_tc_supported(d, k, n_levels) || !make_plan(d, k, n_levels, &plan)) return 0;
+  return static_cast<size_t>(n_levels) * plan.n_ktiles * plan.tile_bytes;
+}
+
+int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream) {
+  TcPlan plan;
+  if (!rq_fwd_tc_supported(d, k, n_levels) || !make_plan(d, k, n_levels, &plan)) {
+    set_error("hv_rq_pack_codebooks: no tcgen05 instantiation for D=%d K=%d L=%d", d, k, n_levels);
+    return HV_ERR_UNSUPPORTED;
+  }
+  const size_t need = static_cast<size_t>(n_levels) * plan.n_ktiles * plan.tile_bytes;
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("hv_rq_pack_codebooks: needs a %zu-byte workspace (got %zu)", need, workspace_bytes);
+    return HV_ERR_WORKSPACE;
+  }
+  if (!aligned16(workspace) || !aligned16(codebooks)) {
+    set_error("hv_rq_pack_codebooks: codebooks and workspace must be 16-byte aligned");
+    return HV_ERR_MISALIGNED;
+  }
+  uint8_t* packed = static_cast<uint8_t*>(workspace);
+  switch (d) {
+    case 16: return pack_d<16>(codebooks, n_levels, k, plan, packed, stream);
+    case 32: return pack_d<32>(codebooks, n_levels, k, plan, packed, stream);
+    case 64: return pack_d<64>(codebooks, n_levels, k, plan, packed, stream);
+    default: return HV_ERR_UNSUPPORTED;
+  }
+}
+
+int launch_rq_fwd_tc(const RqFwdArgs& a, int d, bool rot, void* workspace, size_t workspace_bytes, bool prepacked,
+                     cudaStream_t stream) {
+  TcPlan plan;
+  if (!rq_fwd_tc_supported(d, a.k, a.n_levels) || !make_plan(d, a.k, a.n_levels, &plan)) {
+    set_error("hv_rq_forward: no tcgen05 instantiation for D=%d K=%d L=%d", d, a.k, a.n_levels);
+    return HV_ERR_UNSUPPORTED;
+  }
+  const size_t need = static_cast<size_t>(a.n_levels) * plan.n_ktiles * plan.tile_bytes;
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("hv_rq_forward: tcgen05 path needs a %zu-byte workspace (got %zu)", need, workspace_bytes);
+    return HV_ERR_WORKSPACE;
+  }
+  if (!aligned16(workspace)) {
+    set_error("hv_rq_forward: workspace must be 16-byte aligned");
+    return HV_ERR_MISALIGNED;
+  }
+  if (a.n == 0) return HV_OK;
+  uint8_t* packed = static_cast<uint8_t*>(workspace);
+  switch (d) {
+    case 16: return launch_d<16>(a, rot, plan, packed, prepacked, stream);
+    case 32: return launch_d<32>(a, rot, plan, packed, prepacked, stream);
+    case 64: return launch_d<64>(a, rot, plan, packed, prepacked, stream);
+    default: return HV_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace hv

@@ -1,0 +1,285 @@
+"""PyTorch-facing operators over the C ABI (include/hidvae_b200.h).
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every numeric result comes from
+a kernel in libhidvae_b200.so.  Tensors must live on a CUDA device: there is no CPU path.
+
+Mirrors, per function, the reference call sequence it replaces:
+  rq_forward / RqFunction     modules/quantize.py:106-148 x L levels + modules/h_rqvae.py:515-523,552,572-574
+  kmeans_*                    init/kmeans.py:43-61
+  uniqueness_loss / count     modules/h_rqvae.py:41-105, :645-648
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import (HV_ALGO_AUTO, HV_ALGO_SIMT, HV_ALGO_SIMT_DIFF, HV_ALGO_TCGEN05, HV_ALGO_TCGEN05_PREPACKED,
+                   HV_MODE_ROTATION_TRICK, HV_MODE_STE, HV_OP_RQ_FORWARD, check, lib)
+
+ALGOS = {"auto": HV_ALGO_AUTO, "tcgen05": HV_ALGO_TCGEN05, "simt": HV_ALGO_SIMT, "simt_diff": HV_ALGO_SIMT_DIFF,
+         "tcgen05_prepacked": HV_ALGO_TCGEN05_PREPACKED}
+
+
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*tensors: Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("hidvae_b200 operators run on CUDA tensors only (there is no CPU fallback); "
+                               f"got a tensor on {t.device}")
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _algo(algo) -> int:
+    return ALGOS[algo] if isinstance(algo, str) else int(algo)
+
+
+class RqForwardResult(NamedTuple):
+    ids: Tensor                     # [N, L] int64
+    emb_out: Optional[Tensor]       # [L, N, D]
+    residuals: Optional[Tensor]     # [L, N, D]
+    loss: Optional[Tensor]          # [N]
+    level_loss: Optional[Tensor]    # [L, N]
+    final_residual: Optional[Tensor]  # [N, D]
+
+
+def workspace_bytes(d: int, k: int, n_levels: int) -> int:
+    return int(lib.hv_workspace_bytes(HV_OP_RQ_FORWARD, 0, d, k, n_levels))
+
+
+def pack_codebooks(codebooks: Tensor) -> Optional[Tensor]:
+    """Tensor-core operand image of the effective codebooks [L, K, D] (hv_rq_pack_codebooks), or None when the
+    shape has no tcgen05 instantiation.  Pass it as `packed=` to rq_forward to skip the per-call pack launch."""
+    _require_cuda(codebooks)
+    codebooks = _f32c(codebooks)
+    n_levels, k, d = codebooks.shape
+    nbytes = workspace_bytes(d, k, n_levels)
+    if not nbytes:
+        return None
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=codebooks.device)
+    with torch.cuda.device(codebooks.device):
+        check(lib.hv_rq_pack_codebooks(codebooks.data_ptr(), n_levels, k, d, ws.data_ptr(), nbytes, _stream(codebooks)))
+    return ws
+
+
+def rq_forward(x: Tensor, codebooks: Tensor, mode: int = HV_MODE_STE, training: bool = False, beta: float = 0.25,
+               want_emb: bool = False, want_residuals: bool = False, want_loss: bool = False,
+               want_level_loss: bool = False, want_final_residual: bool = False, algo="auto",
+               ids_out: Optional[Tensor] = None, packed: Optional[Tensor] = None) -> RqForwardResult:
+    """One launch of the fused L-level quantiser (hv_rq_forward).  x [N, D], codebooks [L, K, D] (effective)."""
+    _require_cuda(x, codebooks)
+    x = _f32c(x)
+    codebooks = _f32c(codebooks)
+    if x.dim() != 2 or codebooks.dim() != 3 or x.shape[1] != codebooks.shape[2]:
+        raise ValueError(f"rq_forward: x {tuple(x.shape)} and codebooks {tuple(codebooks.shape)} do not agree")
+    n, d = x.shape
+    n_levels, k, _ = codebooks.shape
+    dev = x.device
+    ids = ids_out if ids_out is not None else torch.empty((n, n_levels), dtype=torch.int64, device=dev)
+    if ids.dtype != torch.int64 or ids.shape != (n, n_levels):
+        raise ValueError("rq_forward: ids_out must be int64 [N, L]")
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    emb = new(n_levels, n, d) if want_emb else None
+    res = new(n_levels, n, d) if want_residuals else None
+    loss = new(n) if want_loss else None
+    level_loss = new(n_levels, n) if want_level_loss else None
+    final = new(n, d) if want_final_residual else None
+    algo = _algo(algo)
+    ws = None
+    ws_bytes = 0
+    if packed is not None:
+        if algo not in (HV_ALGO_AUTO, HV_ALGO_TCGEN05, HV_ALGO_TCGEN05_PREPACKED):
+            raise ValueError("rq_forward: `packed` only applies to the tcgen05 algorithm")
+        algo, ws, ws_bytes = HV_ALGO_TCGEN05_PREPACKED, packed, packed.numel()
+    elif algo in (HV_ALGO_AUTO, HV_ALGO_TCGEN05):
+        ws_bytes = workspace_bytes(d, k, n_levels)
+        if ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.hv_rq_forward(x.data_ptr(), n, d, codebooks.data_ptr(), n_levels, k, int(mode), int(bool(training)),
+                                float(beta), ids.data_ptr(), ids.stride(0), ids.stride(1), _ptr(emb), _ptr(res),
+                                _ptr(loss), _ptr(level_loss), _ptr(final), algo, _ptr(ws), ws_bytes, _stream(x)))
+    return RqForwardResult(ids, emb, res, loss, level_loss, final)
+
+
+def rq_backward(x: Tensor, codebooks: Tensor, ids: Tensor, mode: int, training: bool, beta: float,
+                g_emb: Optional[Tensor], g_loss: Optional[Tensor], g_level_loss: Optional[Tensor]):
+    """hv_rq_backward.  g_emb is indexed [L, N, D] (any strides with unit stride in D), g_loss [N] (any stride),
+    g_level_loss [L, N].  Returns (g_x [N, D], g_codebooks [L, K, D])."""
+    _require_cuda(x, codebooks, ids)
+    x = _f32c(x)
+    codebooks = _f32c(codebooks)
+    n, d = x.shape
+    n_levels, k, _ = codebooks.shape
+    g_x = torch.empty_like(x)
+    g_cb = torch.zeros_like(codebooks)
+    ls = rs = 0
+    if g_emb is not None:
+        if g_emb.dtype != torch.float32:
+            g_emb = g_emb.float()
+        if (g_emb.stride(2) != 1 and d > 1) or g_emb.stride(0) % 4 or g_emb.stride(1) % 4 or g_emb.data_ptr() % 16:
+            g_emb = g_emb.contiguous()
+        ls, rs = g_emb.stride(0), g_emb.stride(1)
+    gl_stride = 0
+    if g_loss is not None:
+        if g_loss.dtype != torch.float32:
+            g_loss = g_loss.float()
+        gl_stride = g_loss.stride(0) if g_loss.dim() else 0
+    if g_level_loss is not None:
+        g_level_loss = _f32c(g_level_loss)
+    with torch.cuda.device(x.device):
+        check(lib.hv_rq_backward(x.data_ptr(), n, d, codebooks.data_ptr(), n_levels, k, int(mode), int(bool(training)),
+                                 float(beta), ids.data_ptr(), ids.stride(0), ids.stride(1), _ptr(g_emb), ls, rs,
+                                 _ptr(g_loss), gl_stride, _ptr(g_level_loss), g_x.data_ptr(), g_cb.data_ptr(),
+                                 _stream(x)))
+    return g_x, g_cb
+
+
+class RqFunction(torch.autograd.Function):
+    """Differentiable fused residual quantiser.
+
+    forward(x [N, D], codebooks [L, K, D], mode, training, beta, algo)
+        -> emb_out [L, N, D], residuals [L, N, D] (not differentiable), ids [N, L], loss [N], level_loss [L, N]
+    backward implements the recursion of SURVEY.md section 8a (autograd of modules/quantize.py:131-148 and
+    modules/h_rqvae.py:552); the forward chain is recomputed, only x, codebooks and ids are saved."""
+
+    @staticmethod
+    def forward(ctx, x, codebooks, mode, training, beta, algo):
+        out = rq_forward(x, codebooks, mode, training, beta, want_emb=True, want_residuals=True, want_loss=True,
+                         want_level_loss=True, algo=algo)
+        ctx.save_for_backward(x, codebooks, out.ids)
+        ctx.cfg = (int(mode), bool(training), float(beta))
+        ctx.mark_non_differentiable(out.ids, out.residuals)
+        return out.emb_out, out.residuals, out.ids, out.loss, out.level_loss
+
+    @staticmethod
+    def backward(ctx, g_emb, _g_res, _g_ids, g_loss, g_level_loss):
+        x, codebooks, ids = ctx.saved_tensors
+        mode, training, beta = ctx.cfg
+        g_x, g_cb = rq_backward(x, codebooks, ids, mode, training, beta, g_emb, g_loss, g_level_loss)
+        return (g_x if ctx.needs_input_grad[0] else None, g_cb if ctx.needs_input_grad[1] else None,
+                None, None, None, None)
+
+
+def rq_apply(x: Tensor, codebooks: Tensor, mode: int, training: bool, beta: float, algo="auto"):
+    """Autograd entry: returns (emb_out [L,N,D], residuals [L,N,D], ids [N,L], loss [N], level_loss [L,N])."""
+    return RqFunction.apply(x, codebooks, int(mode), bool(training), float(beta), algo)
+
+
+def rq_encode(x: Tensor, codebooks: Tensor, algo="auto", ids_out: Optional[Tensor] = None,
+              packed: Optional[Tensor] = None) -> Tensor:
+    """Encode-only (eval) semantic IDs [N, L] -- modules/tokenizer/h_semids.py:127-130."""
+    return rq_forward(x, codebooks, HV_MODE_STE, False, 0.0, algo=algo, ids_out=ids_out, packed=packed).ids
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# k-means (init/kmeans.py)
+# ------------------------------------------------------------------------------------------------------------------
+def kmeans_assign(x: Tensor, centroids: Tensor, exact_diff_form: bool = True) -> Tensor:
+    """argmin_k |x - c_k|^2 -> [N] int64 (init/kmeans.py:44-47).  `exact_diff_form` evaluates sum (x-c)^2 like the
+    reference; otherwise the tensor-core GEMM form is used (same near-tie policy as the quantiser)."""
+    algo = HV_ALGO_SIMT_DIFF if exact_diff_form else HV_ALGO_AUTO
+    return rq_forward(x, centroids.unsqueeze(0), HV_MODE_STE, False, 0.0, algo=algo).ids.view(-1)
+
+
+def kmeans_accumulate(x: Tensor, assign: Tensor, k: int, prev_assign: Optional[Tensor] = None):
+    """Deterministic per-cluster sums [K, D], counts [K] and the number of changed assignments (0-d int64)."""
+    _require_cuda(x, assign)
+    x = _f32c(x)
+    n, d = x.shape
+    sums = torch.empty((k, d), dtype=torch.float32, device=x.device)
+    counts = torch.empty((k,), dtype=torch.float32, device=x.device)
+    changed = torch.empty((), dtype=torch.int64, device=x.device)
+    assign = assign.contiguous()
+    if prev_assign is not None:
+        prev_assign = prev_assign.contiguous()
+    with torch.cuda.device(x.device):
+        check(lib.hv_kmeans_accumulate(x.data_ptr(), n, d, assign.data_ptr(), _ptr(prev_assign), k, sums.data_ptr(),
+                                       counts.data_ptr(), changed.data_ptr(), _stream(x)))
+    return sums, counts, changed
+
+
+def kmeans_finalize(sums: Tensor, counts: Tensor, centroids: Tensor, reseed_rows: Optional[Tensor] = None) -> Tensor:
+    """centroids (in place) <- means / reseeds; returns stats [2] = (max centroid shift, number of empty clusters)."""
+    _require_cuda(sums, counts, centroids)
+    k, d = centroids.shape
+    if not centroids.is_contiguous() or centroids.dtype != torch.float32:
+        raise ValueError("kmeans_finalize: centroids must be contiguous fp32 (updated in place)")
+    stats = torch.empty((2,), dtype=torch.float32, device=centroids.device)
+    if reseed_rows is not None:
+        reseed_rows = _f32c(reseed_rows)
+    with torch.cuda.device(centroids.device):
+        check(lib.hv_kmeans_finalize(sums.data_ptr(), counts.data_ptr(), _ptr(reseed_rows), k, d, centroids.data_ptr(),
+                                     stats.data_ptr(), _stream(centroids)))
+    return stats
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# uniqueness loss / p_unique_ids (modules/h_rqvae.py:41-105, :645-648)
+# ------------------------------------------------------------------------------------------------------------------
+def uniq_stats(ids: Tensor, feats: Optional[Tensor], margin: float) -> Tensor:
+    """stats [3] double: (sum of hinges over identical pairs i<j, number of such pairs, rows with a later twin)."""
+    _require_cuda(ids)
+    if ids.dtype != torch.int64 or ids.dim() != 2:
+        raise ValueError("uniq_stats: ids must be int64 [rows, width]")
+    rows, width = ids.shape
+    d = 0
+    if feats is not None:
+        _require_cuda(feats)
+        feats = _f32c(feats)
+        d = feats.shape[1]
+    stats = torch.empty((3,), dtype=torch.float64, device=ids.device)
+    with torch.cuda.device(ids.device):
+        check(lib.hv_uniq_forward(ids.data_ptr(), rows, width, ids.stride(0), ids.stride(1), _ptr(feats), d,
+                                  float(margin), stats.data_ptr(), _stream(ids)))
+    return stats
+
+
+class UniqFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, ids, margin, weight):
+        feats_c = _f32c(feats)
+        stats = uniq_stats(ids, feats_c, margin)
+        ctx.save_for_backward(feats_c, ids, stats)
+        ctx.cfg = (float(margin), float(weight))
+        pairs = stats[1]
+        mean = torch.where(pairs > 0, stats[0] / pairs.clamp(min=1.0), torch.zeros_like(pairs))
+        return (weight * mean).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        feats, ids, stats = ctx.saved_tensors
+        margin, weight = ctx.cfg
+        g_feats = torch.zeros_like(feats)
+        g = g_out.contiguous().float().reshape(1)
+        rows, width = ids.shape
+        with torch.cuda.device(feats.device):
+            check(lib.hv_uniq_backward(ids.data_ptr(), rows, width, ids.stride(0), ids.stride(1), feats.data_ptr(),
+                                       feats.shape[1], margin, weight, stats.data_ptr(), g.data_ptr(),
+                                       g_feats.data_ptr(), _stream(feats)))
+        return g_feats, None, None, None
+
+
+def uniqueness_loss(ids: Tensor, feats: Tensor, margin: float, weight: float) -> Tensor:
+    """weight * mean_{i<j, ids_i == ids_j} relu(cos(f_i, f_j) - margin); 0 when there is no such pair.
+    `ids` is [rows, width]; no host synchronisation (the reference syncs in torch.where, h_rqvae.py:73)."""
+    return UniqFunction.apply(feats, ids, float(margin), float(weight))
+
+
+def count_rows_with_later_twin(ids: Tensor) -> Tensor:
+    """0-d double tensor: number of rows that have a LATER identical row; p_unique_ids = 1 - this / rows."""
+    return uniq_stats(ids, None, 0.0)[2]

@@ -4,8 +4,10 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+PKG = os.path.join(ROOT, "hid-vae_b200")  # holds hidvae_b200/ and the reference-shaped modules/, init/, data/
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
 

@@ -1,0 +1,269 @@
+"""GPU parity tests of the fused residual quantiser, called through the C ABI (ctypes -> libhidvae_b200.so).
+
+Checker = oracle/ (pinned to the reference by tests/golden) on the same seeded inputs.
+Bars (BASELINE.json north_star / SURVEY.md section 8c):
+  * semantic IDs bit-exact, except rows whose fp32 top-2 distance gap is < 1e-5 relative (tests/helpers.check_ids)
+  * emb_out / residuals / loss / g_x: rtol 1e-5, atol 1e-6 (fp32)
+  * codebook gradient: rtol 1e-4, atol 1e-5 (atomic accumulation order)
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import check_ids, make_codebooks, npz, oracle_levels, t, unit_rows
+from oracle import rq as O
+
+pytestmark = pytest.mark.gpu
+
+MODES = {"ste": O.MODE_STE, "rot": O.MODE_ROTATION_TRICK}
+ALGOS = ["simt", "tcgen05"]
+VAL = dict(rtol=1e-5, atol=1e-6)
+GCB = dict(rtol=1e-4, atol=1e-5)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from hidvae_b200 import ops as _ops
+    return _ops
+
+
+def _dev(x):
+    return x.cuda()
+
+
+def _run_forward(ops, x, cbs, mode, training, beta, algo):
+    return ops.rq_forward(_dev(x), _dev(cbs), mode, training, beta, want_emb=True, want_residuals=True,
+                          want_loss=True, want_level_loss=True, want_final_residual=True, algo=algo)
+
+
+def _compare_values(out, ref, rows):
+    """out: RqForwardResult on GPU ([L,N,D] layout); ref: oracle RqOutput ([N,D,L] layout); rows: bool mask."""
+    emb = out.emb_out.cpu().permute(1, 2, 0)
+    res = out.residuals.cpu().permute(1, 2, 0)
+    torch.testing.assert_close(emb[rows], ref.embeddings[rows], **VAL)
+    torch.testing.assert_close(res[rows], ref.residuals[rows], **VAL)
+    torch.testing.assert_close(out.loss.cpu()[rows], ref.quantize_loss[rows], **VAL)
+    for l, ll in enumerate(ref.level_losses):
+        torch.testing.assert_close(out.level_loss.cpu()[l][rows], ll[rows], **VAL)
+    final_ref = ref.residuals[:, :, -1] - ref.embeddings[:, :, -1]
+    torch.testing.assert_close(out.final_residual.cpu()[rows], final_ref[rows], **VAL)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden fixtures recorded from the real reference
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("mname", ["ste", "rot"])
+@pytest.mark.parametrize("training", [0, 1])
+def test_golden_rq_c1(ops, golden_dir, algo, mname, training):
+    """HRqVae.get_semantic_ids of the reference (modules/h_rqvae.py:481-583), D=32 K=256 L=3, forward + backward."""
+    g = npz(golden_dir, "rq_c1.npz")
+    tag = f"{mname}_train{training}"
+    enc, weights, beta = t(g[f"{tag}/enc"]), t(g[f"{tag}/weights"]), float(g[f"{tag}/beta"])
+    ws = [weights[l].clone().requires_grad_(True) for l in range(weights.shape[0])]
+    cbs = torch.stack([O.effective_codebook(w, normalize=(l == 0)) for l, w in enumerate(ws)])
+    out = _run_forward(ops, enc, cbs.detach(), MODES[mname], bool(training), beta, algo)
+    assert torch.equal(out.ids.cpu(), t(g[f"{tag}/sem_ids"]))
+    torch.testing.assert_close(out.emb_out.cpu().permute(1, 2, 0), t(g[f"{tag}/embeddings"]), **VAL)
+    torch.testing.assert_close(out.residuals.cpu().permute(1, 2, 0), t(g[f"{tag}/residuals"]), **VAL)
+    torch.testing.assert_close(out.loss.cpu(), t(g[f"{tag}/quantize_loss"]), **VAL)
+    # backward through the autograd Function, codebook gradient chained through out_proj by PyTorch
+    x_d = _dev(enc).requires_grad_(True)
+    ws_d = [_dev(w.detach()).requires_grad_(True) for w in ws]
+    cbs_d = torch.stack([O.effective_codebook(w, normalize=(l == 0)) for l, w in enumerate(ws_d)])
+    emb, _res, ids, loss, _ll = ops.rq_apply(x_d, cbs_d, MODES[mname], bool(training), beta, algo=algo)
+    g_emb = _dev(t(g[f"{tag}/g_emb"]))  # [N, D, L]
+    ((emb.permute(1, 2, 0) * g_emb).sum() + (loss * _dev(t(g[f"{tag}/g_loss"]))).sum()).backward()
+    torch.testing.assert_close(x_d.grad.cpu(), t(g[f"{tag}/grad_enc"]), rtol=2e-5, atol=2e-6)
+    for l, w in enumerate(ws_d):
+        torch.testing.assert_close(w.grad.cpu(), t(g[f"{tag}/grad_weights"][l]), **GCB)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("mname", ["ste", "rot"])
+@pytest.mark.parametrize("normalize", [0, 1])
+@pytest.mark.parametrize("training", [0, 1])
+def test_golden_single_level(ops, golden_dir, algo, mname, normalize, training):
+    """One Quantize.forward of the reference (modules/quantize.py:100-154): D=32, K=64, N=48."""
+    g = npz(golden_dir, "quantize_levels.npz")
+    tag = f"{mname}_norm{normalize}_train{training}"
+    x, w, beta = t(g[f"{tag}/x"]), t(g[f"{tag}/weight"]), float(g[f"{tag}/beta"])
+    x_d = _dev(x).requires_grad_(True)
+    w_d = _dev(w).requires_grad_(True)
+    cb = O.effective_codebook(w_d, bool(normalize)).unsqueeze(0)
+    emb, _res, ids, loss, _ll = ops.rq_apply(x_d, cb, MODES[mname], bool(training), beta, algo=algo)
+    assert torch.equal(ids.cpu().view(-1), t(g[f"{tag}/ids"]))
+    torch.testing.assert_close(emb[0].cpu(), t(g[f"{tag}/emb_out"]), **VAL)
+    torch.testing.assert_close(loss.cpu(), t(g[f"{tag}/loss"]), **VAL)
+    ((emb[0] * _dev(t(g[f"{tag}/g_emb"]))).sum() + (loss * _dev(t(g[f"{tag}/g_loss"]))).sum()).backward()
+    torch.testing.assert_close(x_d.grad.cpu(), t(g[f"{tag}/grad_x"]), rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(w_d.grad.cpu(), t(g[f"{tag}/grad_weight"]), **GCB)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle on seeded synthetic inputs (BASELINE.json configs 1 and 4 at oracle-friendly sizes) and edge shapes
+# ---------------------------------------------------------------------------------------------------------------
+SHAPES = [
+    # (n, d, k, L)
+    (1024, 32, 256, 3),   # config 1
+    (2048, 64, 4096, 4),  # config 4 shape, reduced N
+    (1, 32, 256, 3),      # single row (the reference's .squeeze() corner, quantize.py:45)
+    (127, 32, 256, 3),    # ragged: less than one row tile
+    (300, 16, 100, 2),    # K not a multiple of the MMA tile, ragged rows
+    (513, 64, 300, 2),    # K spanning two N tiles with padding
+    (257, 32, 8, 4),      # tiny codebook
+]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("mname,training", [("ste", 1), ("rot", 1), ("rot", 0)])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "n%d_d%d_k%d_L%d" % s)
+def test_forward_vs_oracle(ops, algo, mname, training, shape):
+    n, d, k, L = shape
+    x = unit_rows(n, d, seed=n + d)
+    cbs = make_codebooks(L, k, d, seed=k + L)
+    beta = 0.4
+    out = _run_forward(ops, x, cbs, MODES[mname], bool(training), beta, algo)
+    match = check_ids(out.ids, x, cbs, MODES[mname], beta, bool(training))
+    assert match.float().mean() > 0.995, f"only {float(match.float().mean()):.4f} of rows match on every level"
+    if n == 1 and mname == "rot" and training:
+        return  # the reference's rotation transform squeezes the batch dim at N == 1 (quantize.py:45): ids only
+    ref = oracle_levels(x, cbs, MODES[mname], beta, bool(training))
+    rows = match & (out.ids.cpu() == ref.sem_ids).all(dim=1)
+    _compare_values(out, ref, rows)
+
+
+@pytest.mark.parametrize("algo", ["simt", "simt_diff", "tcgen05"])
+def test_randn_codebooks_large_k(ops, algo):
+    """config 4 variant with randn codebooks."""
+    n, d, k, L = 4096, 64, 4096, 4
+    x = unit_rows(n, d, seed=5)
+    cbs = make_codebooks(L, k, d, seed=6, kind="randn")
+    out = ops.rq_forward(_dev(x), _dev(cbs), O.MODE_STE, False, 0.25, algo=algo)
+    match = check_ids(out.ids, x, cbs, O.MODE_STE, 0.25, False)
+    assert match.float().mean() > 0.995
+
+
+def test_empty_batch(ops):
+    x = torch.empty(0, 32, device="cuda")
+    cbs = _dev(make_codebooks(3, 256, 32, seed=1))
+    out = ops.rq_forward(x, cbs, O.MODE_STE, True, 0.25, want_emb=True, want_loss=True)
+    assert out.ids.shape == (0, 3) and out.emb_out.shape == (3, 0, 32) and out.loss.shape == (0,)
+
+
+def test_exact_ties_take_first_index(ops):
+    """Duplicate code rows: the lowest index must win (torch.min semantics, modules/quantize.py:122)."""
+    d, k = 32, 64
+    cb = make_codebooks(1, k, d, seed=2)
+    cb[0, 40] = cb[0, 7]
+    cb[0, 63] = cb[0, 7]
+    x = cb[0, 7].repeat(200, 1) + 1e-3 * unit_rows(200, d, seed=3)
+    for algo in ALGOS:
+        ids = ops.rq_encode(_dev(x), _dev(cb), algo=algo).cpu().view(-1)
+        assert (ids == 7).all(), algo
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_ids_out_strided(ops, algo):
+    """ids may be written into a caller-provided [N, L] view (e.g. a column block of the [N, L + L_tags] table the
+    tokenizer caches, modules/tokenizer/h_semids.py:134-178)."""
+    n, d, k, L = 500, 32, 256, 3
+    x, cbs = unit_rows(n, d, 9), make_codebooks(L, k, d, 10)
+    table = torch.full((n, L + 2), -1, dtype=torch.int64, device="cuda")
+    ops.rq_encode(_dev(x), _dev(cbs), algo=algo, ids_out=table[:, :L])
+    ref = ops.rq_encode(_dev(x), _dev(cbs), algo=algo)
+    assert torch.equal(table[:, :L], ref) and (table[:, L:] == -1).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# backward
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mname,training", [("ste", 1), ("rot", 1), ("ste", 0)])
+@pytest.mark.parametrize("shape", [(1024, 32, 256, 3), (777, 64, 512, 4), (64, 16, 32, 2)],
+                         ids=lambda s: "n%d_d%d_k%d_L%d" % s)
+def test_backward_vs_oracle_autograd(ops, mname, training, shape):
+    n, d, k, L = shape
+    beta = 0.4
+    x = unit_rows(n, d, seed=21)
+    cbs = make_codebooks(L, k, d, seed=22)
+    gen = torch.Generator().manual_seed(23)
+    g_emb = torch.randn(n, d, L, generator=gen)
+    g_loss = torch.randn(n, generator=gen)
+    g_ll = torch.randn(L, n, generator=gen)
+    # GPU
+    x_d = _dev(x).requires_grad_(True)
+    cb_d = _dev(cbs).requires_grad_(True)
+    emb, _r, ids, loss, level_loss = ops.rq_apply(x_d, cb_d, MODES[mname], bool(training), beta, algo="simt")
+    ((emb.permute(1, 2, 0) * _dev(g_emb)).sum() + (loss * _dev(g_loss)).sum() + (level_loss * _dev(g_ll)).sum()).backward()
+    # oracle autograd on the rows whose ids agree (a near-tie row follows another code and so other gradients)
+    x_o = x.clone().requires_grad_(True)
+    cb_o = [cbs[l].clone().requires_grad_(True) for l in range(L)]
+    ref = O.rq_forward(x_o, cb_o, MODES[mname], beta, bool(training))
+    rows = (ids.cpu() == ref.sem_ids).all(dim=1)
+    assert rows.float().mean() > 0.995
+    m = rows.float()
+    ((ref.embeddings * g_emb * m[:, None, None]).sum() + (ref.quantize_loss * g_loss * m).sum()
+     + sum((ll * g_ll[l] * m).sum() for l, ll in enumerate(ref.level_losses))).backward()
+    torch.testing.assert_close(x_d.grad.cpu()[rows], x_o.grad[rows], rtol=2e-5, atol=2e-6)
+    if bool(rows.all()):
+        for l in range(L):
+            torch.testing.assert_close(cb_d.grad.cpu()[l], cb_o[l].grad, **GCB)
+
+
+def test_backward_broadcast_grad(ops):
+    """The decoder consumes embs.sum(-1) (modules/h_rqvae.py:607): its gradient reaches the kernel as a
+    level-broadcast view (level stride 0), and mean() makes g_loss a stride-0 scalar."""
+    n, d, k, L = 512, 32, 256, 3
+    x, cbs = unit_rows(n, d, 31), make_codebooks(L, k, d, 32)
+    tgt = unit_rows(n, d, 33)
+    x_d = _dev(x).requires_grad_(True)
+    cb_d = _dev(cbs).requires_grad_(True)
+    emb, _r, ids, loss, _ll = ops.rq_apply(x_d, cb_d, O.MODE_ROTATION_TRICK, True, 0.4, algo="simt")
+    (((emb.permute(1, 2, 0).sum(-1) - _dev(tgt)) ** 2).sum() + loss.mean()).backward()
+    x_o = x.clone().requires_grad_(True)
+    cb_o = [cbs[l].clone().requires_grad_(True) for l in range(L)]
+    ref = O.rq_forward(x_o, cb_o, O.MODE_ROTATION_TRICK, 0.4, True)
+    assert torch.equal(ids.cpu(), ref.sem_ids)
+    (((ref.embeddings.sum(-1) - tgt) ** 2).sum() + ref.quantize_loss.mean()).backward()
+    torch.testing.assert_close(x_d.grad.cpu(), x_o.grad, rtol=2e-5, atol=2e-6)
+    for l in range(L):
+        torch.testing.assert_close(cb_d.grad.cpu()[l], cb_o[l].grad, **GCB)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE.json configs 4 and 5 shapes)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(65536, 64, 4096, 4), (1 << 20, 32, 256, 3)], ids=["config4", "config5_chunk"])
+def test_full_size_properties(ops, shape):
+    n, d, k, L = shape
+    x = _dev(unit_rows(n, d, seed=41))
+    cbs = _dev(make_codebooks(L, k, d, seed=42))
+    out = ops.rq_forward(x, cbs, O.MODE_STE, False, 0.25, want_emb=True, want_loss=True, want_final_residual=True,
+                         algo="tcgen05")
+    ids = out.ids
+    assert int(ids.min()) >= 0 and int(ids.max()) < k
+    # (1) reconstruction identity: x - sum_l C_l[id_l] == final residual, emb_out_l == C_l[id_l] (eval semantics)
+    r = x.clone()
+    loss = torch.zeros(n, device="cuda")
+    for l in range(L):
+        e = cbs[l][ids[:, l]]
+        torch.testing.assert_close(out.emb_out[l], e, rtol=0, atol=0)
+        loss += 1.25 * ((r - e) ** 2).sum(-1)
+        r = r - e
+    torch.testing.assert_close(out.final_residual, r, **VAL)
+    torch.testing.assert_close(out.loss, loss, **VAL)
+    # (2) optimality: no code is closer than the chosen one by more than the near-tie allowance (checked with an
+    #     fp32 torch table on a strided sample of rows, level 0)
+    sample = torch.arange(0, n, max(1, n // 8192), device="cuda")
+    table = ((x[sample] ** 2).sum(1, keepdim=True) + (cbs[0] ** 2).sum(1)[None] - 2 * x[sample] @ cbs[0].T)
+    best = table.min(dim=1).values
+    chosen = table.gather(1, ids[sample, :1]).view(-1)
+    assert bool(((chosen - best) <= 1e-5 * best.abs() + 1e-7).all())
+    # (3) the exact-fp32 CUDA-core kernel and the tensor-core kernel agree on (almost) every row
+    ids_simt = ops.rq_encode(x[: 1 << 16], cbs, algo="simt")
+    agree = (ids_simt == ids[: 1 << 16]).all(dim=1).float().mean()
+    assert float(agree) > 0.999, float(agree)
+    # (4) oracle on a 4096-row sample
+    rows = torch.arange(0, n, n // 4096)[:4096]
+    match = check_ids(ids[rows.cuda()], x[rows.cuda()].cpu(), cbs.cpu(), O.MODE_STE, 0.25, False)
+    assert match.float().mean() > 0.995
