@@ -157,6 +157,27 @@ class GradComm:
         torch.cuda.current_stream().wait_stream(self.stream)
 
 
+class GraphedStep:
+    """The step captured once into a CUDA graph and replayed: the C2 step is a handful of microsecond-scale
+    launches, so the CPU-side launch path (ctypes + allocator) would otherwise be what is measured."""
+
+    def __init__(self, fn):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out
+
+
 def time_region(fn, steps, warmup, flush):
     """W warm-ups, then K steps each bracketed by CUDA events on the current stream, L2 flushed between steps."""
     for _ in range(warmup):
@@ -196,8 +217,17 @@ def run_native(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    eager = lambda: step(comm)
+    run_step, graphed = eager, False
+    if not args.no_graph:
+        try:
+            run_step, graphed = GraphedStep(eager), True
+        except Exception as e:  # e.g. a collective that cannot be captured: fall back to eager launches
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            torch.cuda.synchronize()
     t_mark0 = time.time()
-    total_ms = time_region(lambda: step(comm), args.steps, args.warmup, flush)
+    total_ms = time_region(run_step, args.steps, args.warmup, flush)
+    eager_ms = time_region(eager, min(args.steps, 100), 3, flush) / min(args.steps, 100) if graphed else None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -281,7 +311,8 @@ def run_native(args):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32 (argmin scores: bf16x3 split on tcgen05, fp32 accumulate)", data="synthetic",
-                    config=dict(WORKLOAD, parallelism=f"dp{world}", items_per_step_per_gpu=n),
+                    config=dict(WORKLOAD, parallelism=f"dp{world}", items_per_step_per_gpu=n, cuda_graph=graphed,
+                                eager_ms_per_step=eager_ms),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=e2e_ms / args.steps),
                     gpu_launches=NativeStep.LAUNCHES_PER_STEP * args.steps, roofline=roofline, cpu_baseline=cpu,
@@ -390,6 +421,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

@@ -132,6 +132,7 @@ struct TcParams {
   int stages;
   int resident;
   int a_bytes;
+  int tiles_per_cta;  // 2: both epilogue warpgroups own a row tile (throughput); 1: one tile per CTA (small N: more SMs)
 };
 
 // bf16 hi/lo split of one row into the K-major core-matrix layout: chunk kc of row `row` lives at
@@ -154,13 +155,45 @@ __device__ __forceinline__ void stage_a_operand(uint8_t* a_hi, uint8_t* a_lo, in
   }
 }
 
-__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int base, float& best, int& best_k) {
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // FMNMX3: one ALU-pipe op for two compares
+  return d;
+}
+
+// max of 32 floats as a 3-ary tree: 17 independent-ish FMNMX3 instead of a 32-long dependent compare/select chain
+__device__ __forceinline__ float max32(const float (&f)[32]) {
+  float a[11];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float s = __uint_as_float(v[j]);
-    if (s > best) {  // strict: the first (lowest) index wins exact ties, like torch.min on the distances
-      best = s;
-      best_k = base + j;
+  for (int i = 0; i < 10; ++i) a[i] = max3(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+  a[10] = fmaxf(f[30], f[31]);
+  const float b0 = max3(a[0], a[1], a[2]), b1 = max3(a[3], a[4], a[5]), b2 = max3(a[6], a[7], a[8]);
+  const float b3 = fmaxf(a[9], a[10]);
+  return fmaxf(max3(b0, b1, b2), b3);
+}
+
+// Running (max, argmax) over one 32-column chunk of scores held in registers; the first (lowest) index wins exact
+// ties, like torch.min on the distances (modules/quantize.py:122).
+//   phase A  m = max of the chunk (FMNMX3 tree, ALU pipe)
+//   phase B  only if some row of the warp improves: position of the first element equal to m, computed on the FMA
+//            pipe so it does not compete with phase A:  t_j = (f_j - m) * 2^120 + (32 - j)  is (32 - j) where
+//            f_j == m and hugely negative elsewhere; the max of t_j therefore names the first maximiser.
+//            (exact for any two scores that differ by at least 2^-114.)
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int base, float& best, int& best_k) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  const float m = max32(f);
+  const bool better = m > best;  // strict: an earlier chunk keeps exact ties
+  if (__any_sync(0xffffffffu, better)) {
+    const float kBig = 1.329227995784916e36f;  // 2^120
+    float t[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = fmaf(f[j] - m, kBig, static_cast<float>(32 - j));
+    const int loc = 32 - static_cast<int>(max32(t));
+    if (better) {
+      best = m;
+      best_k = base + loc;
     }
   }
 }
@@ -213,10 +246,11 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
   const uint32_t tmem_base = *s_tmem;
 
   const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
-  const int64_t n_pairs = (n_row_tiles + 1) / 2;
+  const int tpc = p.tiles_per_cta;
+  const int64_t n_pairs = (n_row_tiles + tpc - 1) / tpc;  // work items of one CTA iteration ("pair" when tpc == 2)
   const int total_tiles = a.n_levels * p.n_ktiles;
 
-  if (warp < kEpiWarps) {
+  if (warp < kEpiWarps && (warp >> 2) < tpc) {
     // ===================================== epilogue warpgroups ============================================
     const int w = warp >> 2;                       // warpgroup = which row tile of the pair / which accumulator
     const int row_in_tile = threadIdx.x - w * kTileRows;
@@ -231,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
     uint32_t acc_phase = 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int64_t row = (2 * pair + w) * kTileRows + row_in_tile;
+      const int64_t row = (tpc * pair + w) * kTileRows + row_in_tile;
       const bool valid = row < a.n;
       float r[D];
       if (valid) {
@@ -289,6 +323,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
         if (a.final_residual != nullptr) store_row<D>(a.final_residual + row * D, r);
       }
     }
+  } else if (warp < kEpiWarps) {
+    // idle warpgroup of the one-tile-per-CTA configuration
   } else if (warp == kProducerWarp) {
     // ===================================== TMA producer ===================================================
     if (lane == 0) {
@@ -339,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
         const uint32_t b_hi = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
         const uint32_t b_lo = b_hi + (D / 8) * chunk_b;
         const uint32_t b_nrm = b_lo + (D / 8) * chunk_b;
-        for (int w = 0; w < 2; ++w) {
+        for (int w = 0; w < tpc; ++w) {
           if (t == 0) {
             ptx::mbar_wait(ptx::smem_u32(&bar_a_ready[w]), a_phase[w]);
             a_phase[w] ^= 1;
@@ -405,9 +441,11 @@ int launch_d(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, 
   DeviceProps props;
   if (int st = device_props(&props)) return st;
   const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
-  const int64_t n_pairs = (n_row_tiles + 1) / 2;
+  // no more row tiles than SMs: give every tile its own CTA so that more SMs (and the whole ALU of each) work
+  const int tpc = n_row_tiles <= static_cast<int64_t>(props.sm_count) ? 1 : 2;
+  const int64_t n_pairs = (n_row_tiles + tpc - 1) / tpc;
   const unsigned grid = static_cast<unsigned>(n_pairs < props.sm_count ? n_pairs : props.sm_count);
-  TcParams p{packed, plan.ntile, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes};
+  TcParams p{packed, plan.ntile, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes, tpc};
   auto go = [&](auto kernel) -> int {
     HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
     kernel<<<grid, kThreads, plan.smem_bytes, stream>>>(a, p);

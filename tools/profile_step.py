@@ -15,7 +15,7 @@ from hidvae_b200 import ops  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=1 << 20)
-ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--shape", default="32,256,3")
 args = ap.parse_args()
 d, k, L = (int(v) for v in args.shape.split(","))
