@@ -67,7 +67,7 @@ size_t rq_fwd_tc_workspace_bytes(int d, int k, int n_levels);
 // ROT implements modules/quantize.py:34-45,134-140 literally:  o = r - 2 (r.w) w + 2 (r.u) q
 // ---------------------------------------------------------------------------------------------------------
 template <int D, bool ROT>
-__device__ __forceinline__ float rq_level_tail(float (&r)[D], const float (&e)[D], float beta, float* o_out) {
+__device__ __forceinline__ float rq_level_tail_o(float (&r)[D], const float (&e)[D], float beta, float (&o)[D]) {
   float a = 0.f;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
@@ -76,13 +76,8 @@ __device__ __forceinline__ float rq_level_tail(float (&r)[D], const float (&e)[D
   }
   const float level_loss = a + beta * a;
   if constexpr (!ROT) {
-    if (o_out != nullptr) {
 #pragma unroll
-      for (int i = 0; i < D; i += 4)
-        *reinterpret_cast<float4*>(o_out + i) = make_float4(e[i], e[i + 1], e[i + 2], e[i + 3]);
-    }
-#pragma unroll
-    for (int i = 0; i < D; ++i) r[i] = r[i] - e[i];
+    for (int i = 0; i < D; ++i) o[i] = e[i];
   } else {
     float rr = 0.f, ee = 0.f;
 #pragma unroll
@@ -105,7 +100,6 @@ __device__ __forceinline__ float rq_level_tail(float (&r)[D], const float (&e)[D
     const float inv_s = 1.0f / fmaxf(sqrtf(ss), 1e-6f);  // w = (u+q) / max(|u+q|, 1e-6)
     const float rw2 = 2.0f * (rs * inv_s);               // 2 (r.w)
     const float ru2 = 2.0f * ru;                         // 2 (r.u)
-    float o[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const float u = r[i] * inv_r;
@@ -113,13 +107,21 @@ __device__ __forceinline__ float rq_level_tail(float (&r)[D], const float (&e)[D
       const float w = (u + q) * inv_s;
       o[i] = r[i] - rw2 * w + ru2 * q;
     }
-    if (o_out != nullptr) {
+  }
 #pragma unroll
-      for (int i = 0; i < D; i += 4)
-        *reinterpret_cast<float4*>(o_out + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-    }
+  for (int i = 0; i < D; ++i) r[i] = r[i] - o[i];
+  return level_loss;
+}
+
+// same, with emb_out written straight from the owning thread (one 128-bit store per 4 floats) when o_out != null
+template <int D, bool ROT>
+__device__ __forceinline__ float rq_level_tail(float (&r)[D], const float (&e)[D], float beta, float* o_out) {
+  float o[D];
+  const float level_loss = rq_level_tail_o<D, ROT>(r, e, beta, o);
+  if (o_out != nullptr) {
 #pragma unroll
-    for (int i = 0; i < D; ++i) r[i] = r[i] - o[i];
+    for (int i = 0; i < D; i += 4)
+      *reinterpret_cast<float4*>(o_out + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
   }
   return level_loss;
 }

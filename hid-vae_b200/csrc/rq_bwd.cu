@@ -56,8 +56,10 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 
-template <int D, bool ROT, bool SMEM_ACC>
-__global__ void __launch_bounds__(kBwdThreads) rq_bwd_kernel(RqBwdArgs a) {
+// LMAX bounds the per-row register arrays (residual and code of every level): 4 covers every shipped config and
+// keeps the kernel at 3+ CTAs per SM; 8 is the general instantiation.
+template <int D, bool ROT, bool SMEM_ACC, int LMAX>
+__global__ void __launch_bounds__(kBwdThreads, LMAX <= 4 ? 3 : 1) rq_bwd_kernel(RqBwdArgs a) {
   constexpr int LPR = D / 4;  // lanes per row
   constexpr int ROWS_PER_WARP = 32 / LPR;
   extern __shared__ __align__(16) float s_gc[];  // [L, K, D] when SMEM_ACC
@@ -80,16 +82,16 @@ __global__ void __launch_bounds__(kBwdThreads) rq_bwd_kernel(RqBwdArgs a) {
     const bool valid = row < a.n;
     const int64_t rrow = valid ? row : 0;  // keep every lane in the shuffles; mask the stores
 
-    float4 R[kMaxLevels], E[kMaxLevels];
-    float inv_r[kMaxLevels], inv_e[kMaxLevels], inv_s[kMaxLevels];
-    int64_t id[kMaxLevels];
+    float4 R[LMAX], E[LMAX];
+    float inv_r[LMAX], inv_e[LMAX], inv_s[LMAX];
+    int id[LMAX];
     float4 r = __ldg(reinterpret_cast<const float4*>(a.x + rrow * D) + sub);
 #pragma unroll
-    for (int l = 0; l < kMaxLevels; ++l) {
+    for (int l = 0; l < LMAX; ++l) {
       if (l < a.n_levels) {
         int64_t code = a.ids[rrow * a.ids_row_stride + l * a.ids_level_stride];
         code = code < 0 ? 0 : (code >= a.k ? a.k - 1 : code);
-        id[l] = code;
+        id[l] = static_cast<int>(code);
         const float4 e = __ldg(reinterpret_cast<const float4*>(a.codebooks + (static_cast<int64_t>(l) * a.k + code) * D) + sub);
         R[l] = r;
         E[l] = e;
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(kBwdThreads) rq_bwd_kernel(RqBwdArgs a) {
     const float gl_all = a.g_loss != nullptr ? a.g_loss[rrow * a.g_loss_stride] : 0.f;
     float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int l = kMaxLevels - 1; l >= 0; --l) {
+    for (int l = LMAX - 1; l >= 0; --l) {
       if (l < a.n_levels) {
         float gl = gl_all;
         if (a.g_level_loss != nullptr) gl += a.g_level_loss[static_cast<int64_t>(l) * a.n + rrow];
@@ -192,7 +194,7 @@ int launch_d(const RqBwdArgs& a, bool rot, cudaStream_t stream) {
   // the L2-resident [L, K, D] gradient is the default; the shared variant stays selectable for experiments.
   const bool smem_acc = false && acc_bytes <= 100 * 1024 && a.n >= static_cast<int64_t>(props.sm_count) * a.k * 4;
   int64_t ctas = (a.n + rows_per_cta - 1) / rows_per_cta;
-  const int64_t cap = static_cast<int64_t>(props.sm_count) * (smem_acc ? 2 : 8);
+  const int64_t cap = static_cast<int64_t>(props.sm_count) * (smem_acc ? 2 : 16);
   if (ctas > cap) ctas = cap;
   auto go = [&](auto kernel, size_t smem) -> int {
     if (smem > 48 * 1024) HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -200,8 +202,9 @@ int launch_d(const RqBwdArgs& a, bool rot, cudaStream_t stream) {
     HV_CUDA_CHECK(cudaGetLastError());
     return HV_OK;
   };
-  if (smem_acc) return rot ? go(rq_bwd_kernel<D, true, true>, acc_bytes) : go(rq_bwd_kernel<D, false, true>, acc_bytes);
-  return rot ? go(rq_bwd_kernel<D, true, false>, 0) : go(rq_bwd_kernel<D, false, false>, 0);
+  if (smem_acc) return rot ? go(rq_bwd_kernel<D, true, true, kMaxLevels>, acc_bytes) : go(rq_bwd_kernel<D, false, true, kMaxLevels>, acc_bytes);
+  if (a.n_levels <= 4) return rot ? go(rq_bwd_kernel<D, true, false, 4>, 0) : go(rq_bwd_kernel<D, false, false, 4>, 0);
+  return rot ? go(rq_bwd_kernel<D, true, false, kMaxLevels>, 0) : go(rq_bwd_kernel<D, false, false, kMaxLevels>, 0);
 }
 
 }  // namespace

@@ -198,6 +198,66 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int base, fl
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Warp-cooperative row movers.  One thread owns one row (D fp32 = D/4 16-byte units), but a warp-wide 128-bit
+// access in which every lane touches a different row costs 32 L1 wavefronts; so rows travel between global memory
+// and their owner threads through a swizzled transpose in shared memory: global side = each row handled by D/4
+// adjacent lanes (4 wavefronts per instruction at D = 32), owner side = conflict-free 128-bit shared accesses.
+// The scratch is the warpgroup's own A-operand buffer (128 rows x D x 4 bytes), free whenever no MMA is reading
+// it; warp q only touches the slots of its rows [32q, 32q+32), so __syncwarp is the only synchronisation.
+// ---------------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ uint32_t xpose_addr(uint32_t base, int row, int u) {
+  return base + u * (kTileRows * 16) + ((row & ~7) << 4) + (((row ^ u) & 7) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// dst <- row `lane` of the warp's 32 rows; src_of(lr) is the global address of local row lr (nullptr = zeros).
+template <int D, typename SrcOf>
+__device__ __forceinline__ void warp_load_rows(float (&dst)[D], uint32_t scratch, int row0, int lane, SrcOf src_of) {
+  constexpr int U = D / 4, RPI = 32 / U;
+  static_assert(U <= 32 && 32 % U == 0, "row must be 1..32 16-byte units");
+#pragma unroll
+  for (int g = 0; g < 32 / RPI; ++g) {
+    const int lr = g * RPI + lane / U, u = lane % U;
+    const float* src = src_of(lr);
+    const float4 v = src != nullptr ? __ldg(reinterpret_cast<const float4*>(src) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sts128(xpose_addr<D>(scratch, row0 + lr, u), v);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const float4 v = lds128(xpose_addr<D>(scratch, row0 + lane, u));
+    dst[4 * u] = v.x, dst[4 * u + 1] = v.y, dst[4 * u + 2] = v.z, dst[4 * u + 3] = v.w;
+  }
+  __syncwarp();
+}
+
+// row `lane` (src) -> global; dst_of(lr) is the global address of local row lr (nullptr = skip).
+template <int D, typename DstOf>
+__device__ __forceinline__ void warp_store_rows(const float (&src)[D], uint32_t scratch, int row0, int lane, DstOf dst_of) {
+  constexpr int U = D / 4, RPI = 32 / U;
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    sts128(xpose_addr<D>(scratch, row0 + lane, u), make_float4(src[4 * u], src[4 * u + 1], src[4 * u + 2], src[4 * u + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < 32 / RPI; ++g) {
+    const int lr = g * RPI + lane / U, u = lane % U;
+    float* dst = dst_of(lr);
+    const float4 v = lds128(xpose_addr<D>(scratch, row0 + lr, u));
+    if (dst != nullptr) reinterpret_cast<float4*>(dst)[u] = v;
+  }
+  __syncwarp();
+}
+
 template <int D, bool ROT>
 __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -264,19 +324,23 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
     const int n_chunks = p.ntile / 32;
     uint32_t acc_phase = 0;
 
+    const uint32_t scratch = ptx::smem_u32(a_hi);   // transpose scratch = this warpgroup's A buffer (see above)
+    const int row0 = quarter * 32;                  // first tile row of this warp
+
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int64_t row = (tpc * pair + w) * kTileRows + row_in_tile;
+      const int64_t warp_row0 = (tpc * pair + w) * kTileRows + row0;  // global row of the warp's local row 0
+      const int64_t row = warp_row0 + lane;
       const bool valid = row < a.n;
       float r[D];
-      if (valid) {
-        load_row<D>(r, a.x + row * D);
-      } else {
-#pragma unroll
-        for (int i = 0; i < D; ++i) r[i] = 0.f;
-      }
+      warp_load_rows<D>(r, scratch, row0, lane,
+                        [&](int lr) { return warp_row0 + lr < a.n ? a.x + (warp_row0 + lr) * D : nullptr; });
       float total_loss = 0.f;
       for (int l = 0; l < a.n_levels; ++l) {
-        if (valid && a.residuals != nullptr) store_row<D>(a.residuals + (static_cast<int64_t>(l) * a.n + row) * D, r);
+        if (a.residuals != nullptr) {
+          float* base = a.residuals + static_cast<int64_t>(l) * a.n * D;
+          warp_store_rows<D>(r, scratch, row0, lane,
+                             [&](int lr) { return warp_row0 + lr < a.n ? base + (warp_row0 + lr) * D : nullptr; });
+        }
         stage_a_operand<D>(a_hi, a_lo, row_in_tile, r);
         ptx::fence_proxy_async_smem();
         __syncwarp();
@@ -307,11 +371,18 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
         }
         best_k = min(best_k, a.k - 1);
 
+        // every MMA of this level has completed (last acc_full observed): the A buffer is free to be the scratch
         const float* cb = a.codebooks + static_cast<int64_t>(l) * a.k * D;
-        float e[D];
-        load_row<D>(e, cb + static_cast<int64_t>(best_k) * D);
-        float* o_out = (valid && a.emb_out != nullptr) ? a.emb_out + (static_cast<int64_t>(l) * a.n + row) * D : nullptr;
-        const float ll = rq_level_tail<D, ROT>(r, e, a.beta, o_out);
+        float e[D], o[D];
+        warp_load_rows<D>(e, scratch, row0, lane, [&](int lr) {
+          return cb + static_cast<int64_t>(__shfl_sync(0xffffffffu, best_k, lr)) * D;
+        });
+        const float ll = rq_level_tail_o<D, ROT>(r, e, a.beta, o);
+        if (a.emb_out != nullptr) {
+          float* base = a.emb_out + static_cast<int64_t>(l) * a.n * D;
+          warp_store_rows<D>(o, scratch, row0, lane,
+                             [&](int lr) { return warp_row0 + lr < a.n ? base + (warp_row0 + lr) * D : nullptr; });
+        }
         total_loss += ll;
         if (valid) {
           a.ids[row * a.ids_row_stride + l * a.ids_level_stride] = best_k;
@@ -320,8 +391,10 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
       }
       if (valid) {
         if (a.loss != nullptr) a.loss[row] = total_loss;
-        if (a.final_residual != nullptr) store_row<D>(a.final_residual + row * D, r);
       }
+      if (a.final_residual != nullptr)
+        warp_store_rows<D>(r, scratch, row0, lane,
+                           [&](int lr) { return warp_row0 + lr < a.n ? a.final_residual + (warp_row0 + lr) * D : nullptr; });
     }
   } else if (warp < kEpiWarps) {
     // idle warpgroup of the one-tile-per-CTA configuration
