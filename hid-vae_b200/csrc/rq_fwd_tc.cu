@@ -1,21 +1,24 @@
 // tcgen05 variant of the fused L-level residual quantiser (HV_ALGO_TCGEN05) for sm_100a.
 //
-// Mapping (re-derived for B200):
+// Mapping (re-derived for B200 and revised after the first ncu captures, profiles/):
 //   GEMM  M = 128 rows of one row tile (= the 128 TMEM lanes), N = up to 256 codes, reduction = D.
 //   score[row, k] = r.c_k - |c_k|^2 / 2   (argmax == argmin of |r|^2 + |c_k|^2 - 2 r.c_k; |r|^2 is row-constant)
 //   fp32-grade scores from bf16 tensor cores: r = r_hi + r_lo, c = c_hi + c_lo (bf16 each), three products
 //   r_hi.c_hi + r_lo.c_hi + r_hi.c_lo accumulated in the fp32 TMEM accumulator, and -|c|^2/2 folded in as one
-//   more K=16 step (A = [1,1,1,0..], B = the norm split in three bf16 pieces).  3*D/16 + 1 tcgen05.mma per tile.
-//   The codebooks are pre-packed once per launch into the UMMA K-major core-matrix layout and staged by 1-D
-//   bulk TMA copies: resident in shared memory for all L levels when they fit (K=256, D=32, L=3: 120 KB),
+//   more K=16 step (A = [1,1,1,0..], B = the norm split in three bf16 pieces).  3*D/16 + 1 tcgen05.mma per unit.
+//   The codebooks are pre-packed once (hv_rq_pack_codebooks) into the UMMA K-major core-matrix layout and staged
+//   by 1-D bulk TMA copies: resident in shared memory for all L levels when they fit (K=256, D=32, L=3: 120 KB),
 //   otherwise streamed through a ring of stages (K=4096, D=64).
-//   One CTA (persistent, one per SM) works on two row tiles at once: two epilogue warpgroups, each owning one
-//   256-column fp32 accumulator (2 x 256 = all 512 TMEM columns), so the MMAs of one tile overlap the argmin
-//   epilogue of the other.  Warp 8 is the TMA producer, warp 9 allocates TMEM and issues every tcgen05.mma.
-//   Epilogue thread t owns row t of its tile for all L levels: tcgen05.ld (32x32b) hands it whole rows, the
-//   running (max, argmax) stays in registers, then it gathers the fp32 code row, forms emb_out / loss / the next
-//   residual in registers and re-stages the residual (bf16 hi/lo) as the next level's A operand.
-//   The [N, K] score matrix never leaves the SM.
+//
+//   A row's L levels are a strictly serial chain (stage A -> MMA -> argmax scan -> code gather -> residual), each
+//   link latency-bound, so throughput comes from the NUMBER OF ROW TILES IN FLIGHT per SM: the persistent CTA runs
+//   NWG epilogue warpgroups (4 where shared memory allows, else 2), each owning one 128-row tile and one
+//   512/NWG-column fp32 accumulator in TMEM; a level's N tile is processed in units of at most that many columns.
+//   One more warp is the TMA producer, one allocates TMEM and issues every tcgen05.mma, serving whichever
+//   warpgroup is ready first.  Epilogue thread t owns row t of its tile for all L levels: tcgen05.ld (32x32b)
+//   hands it whole rows, the running (max, argmax) stays in registers, then the warp gathers the fp32 code rows,
+//   forms emb_out / loss / the next residual in registers and re-stages the residual (bf16 hi/lo) as the next
+//   level's A operand.  The [N, K] score matrix never leaves the SM.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -23,13 +26,9 @@ namespace hv {
 namespace {
 
 constexpr int kTileRows = 128;
-constexpr int kEpiWarps = 8;
-constexpr int kProducerWarp = 8;
-constexpr int kMmaWarp = 9;
-constexpr int kThreads = 320;
 constexpr int kTmemCols = 512;
-constexpr int kAccCols = 256;
 constexpr int kMaxStages = 16;
+constexpr int kMaxWg = 4;
 constexpr int kOnesBytes = 2 * kTileRows * 16;  // one K=16 step of the A operand: [2 chunks][128 rows][8 bf16]
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -40,17 +39,18 @@ struct TcPlan {
   int stages;      // shared-memory stages for packed images
   int resident;    // 1: every (level, tile) image has its own stage and is loaded once
   int smem_bytes;
-  int a_bytes;     // one warpgroup's A operand (hi + lo)
+  int a_bytes;     // one warpgroup's A operand (hi + lo) == one fp32 row tile
+  int n_wg;        // epilogue warpgroups = row tiles in flight per CTA
 };
 
-bool make_plan(int d, int k, int n_levels, TcPlan* p) {
-  if (d % 16 != 0 || d < 16 || d > 128 || k < 1 || n_levels < 1) return false;
+bool plan_for(int d, int k, int n_levels, int n_wg, TcPlan* p) {
   const int kpad = (k + 31) / 32 * 32;
   p->ntile = kpad <= 256 ? kpad : 256;
   p->n_ktiles = (k + p->ntile - 1) / p->ntile;
   p->tile_bytes = p->ntile * (4 * d + 32);
   p->a_bytes = kTileRows * d * 4;
-  const int fixed = 2 * p->a_bytes + kOnesBytes + 1024;
+  p->n_wg = n_wg;
+  const int fixed = n_wg * p->a_bytes + kOnesBytes + 1024;
   const int budget = kSmemLimit - fixed;
   const int total_tiles = n_levels * p->n_ktiles;
   if (total_tiles <= kMaxStages && static_cast<long long>(total_tiles) * p->tile_bytes <= budget) {
@@ -64,6 +64,14 @@ bool make_plan(int d, int k, int n_levels, TcPlan* p) {
   }
   p->smem_bytes = fixed + p->stages * p->tile_bytes;
   return true;
+}
+
+// The packed image (ntile, tile_bytes) does not depend on n_wg, so pack and forward always agree.
+bool make_plan(int d, int k, int n_levels, TcPlan* p) {
+  if (d % 16 != 0 || d < 16 || d > 128 || k < 1 || n_levels < 1) return false;
+  // four tiles in flight when the whole operand image stays resident beside four A buffers; else two
+  if (plan_for(d, k, n_levels, 4, p) && p->resident) return true;
+  return plan_for(d, k, n_levels, 2, p);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -132,7 +140,7 @@ struct TcParams {
   int stages;
   int resident;
   int a_bytes;
-  int tiles_per_cta;  // 2: both epilogue warpgroups own a row tile (throughput); 1: one tile per CTA (small N: more SMs)
+  int tiles_per_cta;  // active warpgroups (1..NWG): fewer when there are not enough row tiles to fill the SMs
 };
 
 // bf16 hi/lo split of one row into the K-major core-matrix layout: chunk kc of row `row` lives at
@@ -178,8 +186,8 @@ __device__ __forceinline__ float max32(const float (&f)[32]) {
 //   phase B  only if some row of the warp improves: position of the first element equal to m, computed on the FMA
 //            pipe so it does not compete with phase A:  t_j = (f_j - m) * 2^120 + (32 - j)  is (32 - j) where
 //            f_j == m and hugely negative elsewhere; the max of t_j therefore names the first maximiser.
-//            (exact for any two scores that differ by at least 2^-114.)
-__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int base, float& best, int& best_k) {
+//            (exact for any two scores that differ by at least 2^-114.)  t overwrites f: no extra registers.
+__device__ __forceinline__ void scan_chunk(uint32_t (&v)[32], int base, float& best, int& best_k) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -187,10 +195,9 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int base, fl
   const bool better = m > best;  // strict: an earlier chunk keeps exact ties
   if (__any_sync(0xffffffffu, better)) {
     const float kBig = 1.329227995784916e36f;  // 2^120
-    float t[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) t[j] = fmaf(f[j] - m, kBig, static_cast<float>(32 - j));
-    const int loc = 32 - static_cast<int>(max32(t));
+    for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j] - m, kBig, static_cast<float>(32 - j));
+    const int loc = 32 - static_cast<int>(max32(f));
     if (better) {
       best = m;
       best_k = base + loc;
@@ -258,38 +265,81 @@ __device__ __forceinline__ void warp_store_rows(const float (&src)[D], uint32_t 
   __syncwarp();
 }
 
-template <int D, bool ROT>
-__global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcParams p) {
+template <int NWG>
+struct Roles {
+  static constexpr int kEpiWarps = NWG * 4;
+  static constexpr int kProducerWarp = NWG * 4;
+  static constexpr int kMmaWarp = NWG * 4 + 1;
+  // the helper warpgroup (TMA producer, MMA issuer, two idle warps) gives its registers to the epilogue warpgroups
+  static constexpr int kThreads = (NWG * 4 + 4) * 32;
+  static constexpr int kHelperRegs = 56;
+  static constexpr int kEpiRegs = ((2048 - 4 * kHelperRegs) / (NWG * 4)) / 8 * 8 > 232 ? 232 : ((2048 - 4 * kHelperRegs) / (NWG * 4)) / 8 * 8;
+  static constexpr int kAccCols = kTmemCols / NWG;  // fp32 accumulator columns of one warpgroup
+};
+
+// issue the 3*D/16 + 1 MMAs of one unit (`ncols` codes starting at code `col0` of the staged N tile)
+template <int D>
+__device__ __forceinline__ void issue_unit(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t ones, uint32_t b_tile,
+                                           int ntile, int col0, int ncols, uint32_t bar_full) {
+  const uint32_t idesc = ptx::umma_idesc_bf16(kTileRows, ncols);
+  const uint32_t chunk_b = ntile * 16;      // bytes between K chunks of the B image
+  const uint32_t chunk_a = kTileRows * 16;  // bytes between K chunks of the A operand
+  const uint32_t b_hi = b_tile + col0 * 16;
+  const uint32_t b_lo = b_hi + (D / 8) * chunk_b;
+  const uint32_t b_nrm = b_lo + (D / 8) * chunk_b;
+  uint32_t accumulate = 0;
+#pragma unroll
+  for (int j = 0; j < D / 16; ++j) {  // r_hi . c_hi
+    ptx::umma_bf16(acc, ptx::umma_smem_desc(a_hi + j * 2 * chunk_a, chunk_a, 128),
+                   ptx::umma_smem_desc(b_hi + j * 2 * chunk_b, chunk_b, 128), idesc, accumulate);
+    accumulate = 1;
+  }
+#pragma unroll
+  for (int j = 0; j < D / 16; ++j)  // r_lo . c_hi
+    ptx::umma_bf16(acc, ptx::umma_smem_desc(a_lo + j * 2 * chunk_a, chunk_a, 128),
+                   ptx::umma_smem_desc(b_hi + j * 2 * chunk_b, chunk_b, 128), idesc, 1);
+#pragma unroll
+  for (int j = 0; j < D / 16; ++j)  // r_hi . c_lo
+    ptx::umma_bf16(acc, ptx::umma_smem_desc(a_hi + j * 2 * chunk_a, chunk_a, 128),
+                   ptx::umma_smem_desc(b_lo + j * 2 * chunk_b, chunk_b, 128), idesc, 1);
+  // 1 * (-|c|^2 / 2)
+  ptx::umma_bf16(acc, ptx::umma_smem_desc(ones, chunk_a, 128), ptx::umma_smem_desc(b_nrm, chunk_b, 128), idesc, 1);
+  ptx::umma_commit(bar_full);
+}
+
+template <int D, bool ROT, int NWG>
+__global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcParams p) {
+  using R = Roles<NWG>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  // [A wg0 hi | A wg0 lo | A wg1 hi | A wg1 lo | ones | barriers (1 KB) | B stages ...]
+  // [A wg0 (hi | lo) | ... | A wg(NWG-1) | ones | barriers (1 KB) | B stages ...]
   uint8_t* s_a = smem;
-  uint8_t* s_ones = smem + 2 * p.a_bytes;
+  uint8_t* s_ones = smem + NWG * p.a_bytes;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ones + kOnesBytes);
   uint8_t* s_b = s_ones + kOnesBytes + 1024;
 
-  uint64_t* bar_b_full = s_bar;                     // [kMaxStages]
-  uint64_t* bar_b_empty = s_bar + kMaxStages;       // [kMaxStages]
-  uint64_t* bar_a_ready = s_bar + 2 * kMaxStages;   // [2]
-  uint64_t* bar_acc_full = bar_a_ready + 2;         // [2]
-  uint64_t* bar_acc_empty = bar_acc_full + 2;       // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  uint64_t* bar_b_full = s_bar;                       // [kMaxStages]
+  uint64_t* bar_b_empty = s_bar + kMaxStages;         // [kMaxStages]
+  uint64_t* bar_a_ready = s_bar + 2 * kMaxStages;     // [kMaxWg]
+  uint64_t* bar_acc_full = bar_a_ready + kMaxWg;      // [kMaxWg]
+  uint64_t* bar_acc_empty = bar_acc_full + kMaxWg;    // [kMaxWg]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + kMaxWg);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == kProducerWarp && lane == 0) {
+  if (warp == R::kProducerWarp && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_b_full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bar_b_empty[s]), 1);
     }
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < kMaxWg; ++w) {
       ptx::mbar_init(ptx::smem_u32(&bar_a_ready[w]), 4);
       ptx::mbar_init(ptx::smem_u32(&bar_acc_full[w]), 1);
       ptx::mbar_init(ptx::smem_u32(&bar_acc_empty[w]), 4);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == kMmaWarp) {
+  if (warp == R::kMmaWarp) {
     ptx::tmem_alloc(ptx::smem_u32(s_tmem), kTmemCols);
     ptx::tmem_relinquish();
   }
@@ -307,28 +357,29 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
 
   const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
   const int tpc = p.tiles_per_cta;
-  const int64_t n_pairs = (n_row_tiles + tpc - 1) / tpc;  // work items of one CTA iteration ("pair" when tpc == 2)
+  const int64_t n_groups = (n_row_tiles + tpc - 1) / tpc;  // one CTA iteration handles a group of tpc row tiles
   const int total_tiles = a.n_levels * p.n_ktiles;
+  const int units_per_tile = (p.ntile + R::kAccCols - 1) / R::kAccCols;
 
-  if (warp < kEpiWarps && (warp >> 2) < tpc) {
+  if (warp < R::kEpiWarps) {
+    ptx::setmaxnreg_inc<R::kEpiRegs>();  // registers handed over by the helper warpgroup below
+    if ((warp >> 2) < tpc) {
     // ===================================== epilogue warpgroups ============================================
-    const int w = warp >> 2;                       // warpgroup = which row tile of the pair / which accumulator
+    const int w = warp >> 2;                       // warpgroup = which row tile of the group / which accumulator
     const int row_in_tile = threadIdx.x - w * kTileRows;
     const int quarter = warp & 3;                  // TMEM lanes [32*quarter, 32*quarter + 32)
     uint8_t* a_hi = s_a + w * p.a_bytes;
     uint8_t* a_lo = a_hi + p.a_bytes / 2;
-    const uint32_t acc_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + w * kAccCols;
+    const uint32_t acc_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + w * R::kAccCols;
     const uint32_t bar_ready = ptx::smem_u32(&bar_a_ready[w]);
     const uint32_t bar_full = ptx::smem_u32(&bar_acc_full[w]);
     const uint32_t bar_empty = ptx::smem_u32(&bar_acc_empty[w]);
-    const int n_chunks = p.ntile / 32;
     uint32_t acc_phase = 0;
-
     const uint32_t scratch = ptx::smem_u32(a_hi);   // transpose scratch = this warpgroup's A buffer (see above)
     const int row0 = quarter * 32;                  // first tile row of this warp
 
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int64_t warp_row0 = (tpc * pair + w) * kTileRows + row0;  // global row of the warp's local row 0
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+      const int64_t warp_row0 = (tpc * grp + w) * kTileRows + row0;  // global row of the warp's local row 0
       const int64_t row = warp_row0 + lane;
       const bool valid = row < a.n;
       float r[D];
@@ -349,25 +400,22 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
         float best = -INFINITY;
         int best_k = 0;
         for (int t = 0; t < p.n_ktiles; ++t) {
-          ptx::mbar_wait(bar_full, acc_phase);
-          acc_phase ^= 1;
-          ptx::tc_fence_after_sync();
-          const int col0 = t * p.ntile;
-          uint32_t v0[32], v1[32];
-          ptx::tmem_ld_32x32(acc_addr, v0);
-          for (int c = 0; c < n_chunks; c += 2) {
-            ptx::tmem_wait_ld(v0);
-            if (c + 1 < n_chunks) ptx::tmem_ld_32x32(acc_addr + (c + 1) * 32, v1);
-            scan_chunk(v0, col0 + c * 32, best, best_k);
-            if (c + 1 < n_chunks) {
-              ptx::tmem_wait_ld(v1);
-              if (c + 2 < n_chunks) ptx::tmem_ld_32x32(acc_addr + (c + 2) * 32, v0);
-              scan_chunk(v1, col0 + (c + 1) * 32, best, best_k);
+          for (int u = 0; u < units_per_tile; ++u) {
+            const int col0 = u * R::kAccCols;
+            const int n_chunks = min(R::kAccCols, p.ntile - col0) / 32;
+            ptx::mbar_wait(bar_full, acc_phase);
+            acc_phase ^= 1;
+            ptx::tc_fence_after_sync();
+            for (int c = 0; c < n_chunks; ++c) {
+              uint32_t v[32];
+              ptx::tmem_ld_32x32(acc_addr + c * 32, v);
+              ptx::tmem_wait_ld(v);
+              scan_chunk(v, t * p.ntile + col0 + c * 32, best, best_k);
             }
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar_empty);
           }
-          ptx::tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_empty);
         }
         best_k = min(best_k, a.k - 1);
 
@@ -389,20 +437,19 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
           if (a.level_loss != nullptr) a.level_loss[static_cast<int64_t>(l) * a.n + row] = ll;
         }
       }
-      if (valid) {
-        if (a.loss != nullptr) a.loss[row] = total_loss;
-      }
+      if (valid && a.loss != nullptr) a.loss[row] = total_loss;
       if (a.final_residual != nullptr)
         warp_store_rows<D>(r, scratch, row0, lane,
                            [&](int lr) { return warp_row0 + lr < a.n ? a.final_residual + (warp_row0 + lr) * D : nullptr; });
     }
-  } else if (warp < kEpiWarps) {
-    // idle warpgroup of the one-tile-per-CTA configuration
-  } else if (warp == kProducerWarp) {
+    }  // else: warpgroup without a row tile (small N: fewer tiles per CTA so that more SMs work)
+  } else {
+    ptx::setmaxnreg_dec<R::kHelperRegs>();
+    if (warp == R::kProducerWarp) {
     // ===================================== TMA producer ===================================================
     if (lane == 0) {
       if (p.resident) {
-        if (static_cast<int64_t>(blockIdx.x) < n_pairs) {
+        if (static_cast<int64_t>(blockIdx.x) < n_groups) {
           for (int s = 0; s < total_tiles; ++s) {
             const uint32_t bar = ptx::smem_u32(&bar_b_full[s]);
             ptx::mbar_arrive_expect_tx(bar, p.tile_bytes);
@@ -412,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
         }
       } else {
         uint32_t it = 0;
-        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
           for (int tile = 0; tile < total_tiles; ++tile, ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1;
@@ -425,73 +472,104 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
         }
       }
     }
-  } else {
+    } else if (warp == R::kMmaWarp) {
     // ===================================== MMA issuer =====================================================
-    const uint32_t idesc = ptx::umma_idesc_bf16(kTileRows, p.ntile);
-    const uint32_t chunk_b = p.ntile * 16;        // bytes between K chunks of the B image
-    const uint32_t chunk_a = kTileRows * 16;      // bytes between K chunks of the A operand
-    uint32_t it = 0;
-    uint32_t a_phase[2] = {0, 0};
-    uint32_t acc_uses[2] = {0, 0};
-    bool first_pair = true;
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      for (int tile = 0; tile < total_tiles; ++tile, ++it) {
-        const int t = tile % p.n_ktiles;
-        int s;
-        if (p.resident) {
-          s = tile;
-          if (first_pair) ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), 0);
-        } else {
-          s = it % p.stages;
-          ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), (it / p.stages) & 1);
-        }
-        const uint32_t b_hi = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
-        const uint32_t b_lo = b_hi + (D / 8) * chunk_b;
-        const uint32_t b_nrm = b_lo + (D / 8) * chunk_b;
-        for (int w = 0; w < tpc; ++w) {
-          if (t == 0) {
-            ptx::mbar_wait(ptx::smem_u32(&bar_a_ready[w]), a_phase[w]);
-            a_phase[w] ^= 1;
-          }
-          ptx::mbar_wait(ptx::smem_u32(&bar_acc_empty[w]), (acc_uses[w] & 1) ^ 1);
-          acc_uses[w]++;
+    const uint32_t ones = ptx::smem_u32(s_ones);
+    if (p.resident) {
+      // Every operand image is resident: the warpgroups are independent, so serve whichever one is ready
+      // (its residual staged and its accumulator drained) instead of a fixed round that blocks on the slowest.
+      if (static_cast<int64_t>(blockIdx.x) < n_groups)
+        for (int s = 0; s < total_tiles; ++s) ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), 0);
+      const int64_t my_groups = static_cast<int64_t>(blockIdx.x) < n_groups
+                                    ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+      const int units_per_level = p.n_ktiles * units_per_tile;
+      const int64_t units_per_wg = my_groups * a.n_levels * units_per_level;
+      int64_t done[kMaxWg] = {0, 0, 0, 0};   // units issued so far, per warpgroup
+      uint32_t a_seen[kMaxWg] = {0, 0, 0, 0};  // levels whose staged residual has been observed
+      int remaining = tpc;
+      long long idle_since = 0;
+      while (remaining > 0) {
+        bool progressed = false;
+#pragma unroll
+        for (int w = 0; w < NWG; ++w) {
+          if (w >= tpc || done[w] >= units_per_wg) continue;
+          const int64_t in_level = done[w] % units_per_level;
+          const int level = static_cast<int>((done[w] / units_per_level) % a.n_levels);
+          const int64_t level_seq = done[w] / units_per_level;   // how many levels of this warpgroup are behind us
+          bool ok = true;
+          if (in_level == 0 && a_seen[w] == level_seq)
+            ok = ptx::mbar_try_wait(ptx::smem_u32(&bar_a_ready[w]), static_cast<uint32_t>(level_seq & 1));
+          ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+          if (!ok) continue;
+          if (in_level == 0 && a_seen[w] == level_seq) a_seen[w]++;
+          ok = ptx::mbar_try_wait(ptx::smem_u32(&bar_acc_empty[w]), static_cast<uint32_t>((done[w] & 1) ^ 1));
+          ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+          if (!ok) continue;
           ptx::tc_fence_after_sync();
           if (lane == 0) {
-            const uint32_t acc = tmem_base + w * kAccCols;
+            const int t = static_cast<int>(in_level / units_per_tile), u = static_cast<int>(in_level % units_per_tile);
+            const int col0 = u * R::kAccCols;
+            const int ncols = min(R::kAccCols, p.ntile - col0);
             const uint32_t a_hi = ptx::smem_u32(s_a + w * p.a_bytes);
-            const uint32_t a_lo = a_hi + p.a_bytes / 2;
-            uint32_t accumulate = 0;
-#pragma unroll
-            for (int j = 0; j < D / 16; ++j) {  // r_hi . c_hi
-              ptx::umma_bf16(acc, ptx::umma_smem_desc(a_hi + j * 2 * chunk_a, chunk_a, 128),
-                             ptx::umma_smem_desc(b_hi + j * 2 * chunk_b, chunk_b, 128), idesc, accumulate);
-              accumulate = 1;
-            }
-#pragma unroll
-            for (int j = 0; j < D / 16; ++j)  // r_lo . c_hi
-              ptx::umma_bf16(acc, ptx::umma_smem_desc(a_lo + j * 2 * chunk_a, chunk_a, 128),
-                             ptx::umma_smem_desc(b_hi + j * 2 * chunk_b, chunk_b, 128), idesc, 1);
-#pragma unroll
-            for (int j = 0; j < D / 16; ++j)  // r_hi . c_lo
-              ptx::umma_bf16(acc, ptx::umma_smem_desc(a_hi + j * 2 * chunk_a, chunk_a, 128),
-                             ptx::umma_smem_desc(b_lo + j * 2 * chunk_b, chunk_b, 128), idesc, 1);
-            // 1 * (-|c|^2 / 2)
-            ptx::umma_bf16(acc, ptx::umma_smem_desc(ptx::smem_u32(s_ones), chunk_a, 128),
-                           ptx::umma_smem_desc(b_nrm, chunk_b, 128), idesc, 1);
-            ptx::umma_commit(ptx::smem_u32(&bar_acc_full[w]));
+            issue_unit<D>(tmem_base + w * R::kAccCols, a_hi, a_hi + p.a_bytes / 2, ones,
+                          ptx::smem_u32(s_b + static_cast<size_t>(level * p.n_ktiles + t) * p.tile_bytes), p.ntile, col0, ncols,
+                          ptx::smem_u32(&bar_acc_full[w]));
           }
           __syncwarp();
+          done[w]++;
+          if (done[w] >= units_per_wg) remaining--;
+          progressed = true;
         }
-        if (!p.resident && lane == 0) ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
-        __syncwarp();
+        if (progressed) {
+          idle_since = 0;
+        } else {
+          if (idle_since == 0) idle_since = clock64();
+          if (clock64() - idle_since > 4000000000LL) {
+            if (lane == 0) printf("hidvae_b200: MMA scheduler starved (block %d)\n", blockIdx.x);
+            __trap();
+          }
+        }
       }
-      first_pair = false;
+    } else {
+      // Streamed operand images: all warpgroups consume the same stage in lock step (one load serves tpc tiles).
+      uint32_t it = 0;
+      uint32_t a_phase[kMaxWg] = {0, 0, 0, 0};
+      uint32_t acc_uses[kMaxWg] = {0, 0, 0, 0};
+      for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        for (int tile = 0; tile < total_tiles; ++tile, ++it) {
+          const int t = tile % p.n_ktiles;
+          const int s = it % p.stages;
+          ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), (it / p.stages) & 1);
+          const uint32_t b_tile = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
+          for (int w = 0; w < tpc; ++w) {
+            if (t == 0) {
+              ptx::mbar_wait(ptx::smem_u32(&bar_a_ready[w]), a_phase[w]);
+              a_phase[w] ^= 1;
+            }
+            for (int u = 0; u < units_per_tile; ++u) {
+              ptx::mbar_wait(ptx::smem_u32(&bar_acc_empty[w]), (acc_uses[w] & 1) ^ 1);
+              acc_uses[w]++;
+              ptx::tc_fence_after_sync();
+              if (lane == 0) {
+                const int col0 = u * R::kAccCols;
+                const uint32_t a_hi = ptx::smem_u32(s_a + w * p.a_bytes);
+                issue_unit<D>(tmem_base + w * R::kAccCols, a_hi, a_hi + p.a_bytes / 2, ones, b_tile, p.ntile, col0,
+                              min(R::kAccCols, p.ntile - col0), ptx::smem_u32(&bar_acc_full[w]));
+              }
+              __syncwarp();
+            }
+          }
+          if (lane == 0) ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
+          __syncwarp();
+        }
+      }
+    }
     }
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == R::kMmaWarp) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -506,26 +584,31 @@ int pack_d(const float* codebooks, int n_levels, int k, const TcPlan& plan, uint
   return HV_OK;
 }
 
+template <int D, int NWG>
+int launch_wg(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, const DeviceProps& props, cudaStream_t stream) {
+  const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
+  // as many row tiles per CTA as it takes to cover them with one CTA per SM, at most NWG
+  int64_t tpc = (n_row_tiles + props.sm_count - 1) / props.sm_count;
+  tpc = tpc < 1 ? 1 : (tpc > NWG ? NWG : tpc);
+  const int64_t n_groups = (n_row_tiles + tpc - 1) / tpc;
+  const unsigned grid = static_cast<unsigned>(n_groups < props.sm_count ? n_groups : props.sm_count);
+  TcParams p{packed, plan.ntile, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes, static_cast<int>(tpc)};
+  auto go = [&](auto kernel) -> int {
+    HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    kernel<<<grid, Roles<NWG>::kThreads, plan.smem_bytes, stream>>>(a, p);
+    HV_CUDA_CHECK(cudaGetLastError());
+    return HV_OK;
+  };
+  return rot ? go(rq_fwd_tc_kernel<D, true, NWG>) : go(rq_fwd_tc_kernel<D, false, NWG>);
+}
+
 template <int D>
 int launch_d(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, bool prepacked, cudaStream_t stream) {
   if (!prepacked)
     if (int st = pack_d<D>(a.codebooks, a.n_levels, a.k, plan, packed, stream)) return st;
-
   DeviceProps props;
   if (int st = device_props(&props)) return st;
-  const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
-  // no more row tiles than SMs: give every tile its own CTA so that more SMs (and the whole ALU of each) work
-  const int tpc = n_row_tiles <= static_cast<int64_t>(props.sm_count) ? 1 : 2;
-  const int64_t n_pairs = (n_row_tiles + tpc - 1) / tpc;
-  const unsigned grid = static_cast<unsigned>(n_pairs < props.sm_count ? n_pairs : props.sm_count);
-  TcParams p{packed, plan.ntile, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes, tpc};
-  auto go = [&](auto kernel) -> int {
-    HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-    kernel<<<grid, kThreads, plan.smem_bytes, stream>>>(a, p);
-    HV_CUDA_CHECK(cudaGetLastError());
-    return HV_OK;
-  };
-  return rot ? go(rq_fwd_tc_kernel<D, true>) : go(rq_fwd_tc_kernel<D, false>);
+  return plan.n_wg == 4 ? launch_wg<D, 4>(a, rot, plan, packed, props, stream) : launch_wg<D, 2>(a, rot, plan, packed, props, stream);
 }
 
 }  // namespace

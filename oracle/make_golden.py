@@ -166,6 +166,58 @@ def make_kmeans_cases(ref):
     np.savez_compressed(os.path.join(OUT, "kmeans.npz"), **out)
 
 
+def make_hrqvae_forward_cases(ref):
+    """Whole `HRqVae.forward` of the reference (modules/h_rqvae.py:585-672) with tags, plus its state_dict, so the
+    drop-in module can be loaded with the reference's weights and compared output by output.  Dropout is 0 and mixup
+    is off so that the training-mode case is deterministic."""
+    Q, H, S = ref.quantize, ref.h_rqvae, ref.schemas
+    out = {}
+    for mname, mode in {"ste": Q.QuantizeForwardMode.STE, "rot": Q.QuantizeForwardMode.ROTATION_TRICK}.items():
+        for training in (True, False):
+            torch.manual_seed(17)
+            gen = torch.Generator().manual_seed(17)
+            n, din, d, k, L, tdim = 96, 64, 32, 64, 3, 16
+            counts = [5, 7, 9]
+            model = H.HRqVae(input_dim=din, embed_dim=d, hidden_dims=[48, 40], codebook_size=k,
+                             codebook_kmeans_init=False, codebook_normalize=True, codebook_mode=mode, n_layers=L,
+                             commitment_weight=0.4, n_cat_features=0, tag_alignment_weight=0.15,
+                             tag_prediction_weight=0.55, tag_class_counts=counts, tag_embed_dim=tdim,
+                             use_focal_loss=True, focal_loss_params={"gamma": 2.7, "alpha": 0.24}, dropout_rate=0.0,
+                             sem_id_uniqueness_weight=1.5, sem_id_uniqueness_margin=0.0)
+            model.tag_prediction_loss.use_mixup = False
+            with torch.no_grad():
+                model.layers[1].embedding.weight.mul_(0.3).sub_(0.15)
+                model.layers[2].embedding.weight.mul_(0.12).sub_(0.06)
+            model.train(training)
+            x = unit_rows(n, din, gen)
+            tags_emb = torch.randn(n, L, tdim, generator=gen)
+            tags_idx = torch.stack([torch.randint(0, c, (n,), generator=gen) for c in counts], dim=1)
+            tags_idx[::11, 1] = -1
+            batch = S.TaggedSeqBatch(None, None, None, x, None, None, tags_emb, tags_idx)
+            res = model(batch, gumbel_t=0.2)
+            tag = f"{mname}_train{int(training)}"
+            if training:
+                res.loss.backward()
+                for key in ("encoder.mlp.0.weight", "decoder.mlp.4.weight", "layers.0.embedding.weight",
+                            "layers.2.embedding.weight", "tag_predictors.1.classifier.7.weight", "tag_projectors.0.0.weight"):
+                    out[f"{tag}/grad/{key}"] = _np(dict(model.named_parameters())[key].grad)
+            for key, val in model.state_dict().items():
+                out[f"{tag}/state/{key}"] = _np(val)
+            out.update({f"{tag}/x": _np(x), f"{tag}/tags_emb": _np(tags_emb), f"{tag}/tags_indices": _np(tags_idx),
+                        f"{tag}/loss": _np(res.loss), f"{tag}/reconstruction_loss": _np(res.reconstruction_loss),
+                        f"{tag}/rqvae_loss": _np(res.rqvae_loss), f"{tag}/tag_align_loss": _np(res.tag_align_loss),
+                        f"{tag}/tag_pred_loss": _np(res.tag_pred_loss), f"{tag}/tag_pred_accuracy": _np(res.tag_pred_accuracy),
+                        f"{tag}/embs_norm": _np(res.embs_norm), f"{tag}/p_unique_ids": _np(res.p_unique_ids),
+                        f"{tag}/sem_id_uniqueness_loss": _np(res.sem_id_uniqueness_loss),
+                        f"{tag}/tag_pred_loss_by_layer": _np(res.tag_pred_loss_by_layer)})
+            with torch.no_grad():
+                model.eval()
+                q = model.get_semantic_ids(model.encode(x))
+                out[f"{tag}/eval_sem_ids"] = _np(q.sem_ids)
+                out[f"{tag}/eval_tag_predictions"] = _np(model.predict_tags(x)["predictions"])
+    np.savez_compressed(os.path.join(OUT, "hrqvae_forward.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order for the recorded values
@@ -174,6 +226,9 @@ def main():
     make_rq_cases(ref)
     make_uniqueness_cases(ref)
     make_kmeans_cases(ref)
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        make_hrqvae_forward_cases(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
