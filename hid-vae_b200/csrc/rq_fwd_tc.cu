@@ -272,8 +272,14 @@ struct Roles {
   static constexpr int kMmaWarp = NWG * 4 + 1;
   // the helper warpgroup (TMA producer, MMA issuer, two idle warps) gives its registers to the epilogue warpgroups
   static constexpr int kThreads = (NWG * 4 + 4) * 32;
+  // setmaxnreg only MOVES registers inside the CTA's launch allocation (kLaunchRegs per thread, what ptxas assigns
+  // under __launch_bounds__(kThreads, 1)); asking for more leaves some warps spinning in the allocation forever.
+  // launch_wg() checks kLaunchRegs against cudaFuncGetAttributes before every launch.
+  static constexpr int kWarps = NWG * 4 + 4;
+  static constexpr int kLaunchRegs = NWG == 4 ? 96 : 168;
   static constexpr int kHelperRegs = 56;
-  static constexpr int kEpiRegs = ((2048 - 4 * kHelperRegs) / (NWG * 4)) / 8 * 8 > 232 ? 232 : ((2048 - 4 * kHelperRegs) / (NWG * 4)) / 8 * 8;
+  static constexpr int kEpiRegs = ((kLaunchRegs * kWarps - 4 * kHelperRegs) / (NWG * 4)) / 8 * 8;
+  static_assert(kEpiRegs * NWG * 4 + kHelperRegs * 4 <= kLaunchRegs * kWarps, "register hand-over exceeds the launch allocation");
   static constexpr int kAccCols = kTmemCols / NWG;  // fp32 accumulator columns of one warpgroup
 };
 
@@ -594,6 +600,13 @@ int launch_wg(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed,
   const unsigned grid = static_cast<unsigned>(n_groups < props.sm_count ? n_groups : props.sm_count);
   TcParams p{packed, plan.ntile, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes, static_cast<int>(tpc)};
   auto go = [&](auto kernel) -> int {
+    cudaFuncAttributes attr;
+    HV_CUDA_CHECK(cudaFuncGetAttributes(&attr, kernel));
+    if (attr.numRegs < Roles<NWG>::kLaunchRegs) {  // would deadlock in setmaxnreg.inc: refuse loudly instead
+      set_error("hv_rq_forward: tcgen05 kernel was built with %d registers/thread, the register hand-over needs %d",
+                attr.numRegs, Roles<NWG>::kLaunchRegs);
+      return HV_ERR_UNSUPPORTED;
+    }
     HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
     kernel<<<grid, Roles<NWG>::kThreads, plan.smem_bytes, stream>>>(a, p);
     HV_CUDA_CHECK(cudaGetLastError());
