@@ -489,9 +489,15 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
       const int64_t my_groups = static_cast<int64_t>(blockIdx.x) < n_groups
                                     ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
       const int units_per_level = p.n_ktiles * units_per_tile;
-      const int64_t units_per_wg = my_groups * a.n_levels * units_per_level;
-      int64_t done[kMaxWg] = {0, 0, 0, 0};   // units issued so far, per warpgroup
-      uint32_t a_seen[kMaxWg] = {0, 0, 0, 0};  // levels whose staged residual has been observed
+      const uint32_t units_per_wg = static_cast<uint32_t>(my_groups * a.n_levels * units_per_level);
+      // per-warpgroup progress, kept in registers (the loops over w are fully unrolled)
+      uint32_t done[NWG];     // units issued so far
+      uint32_t in_level[NWG]; // position of the next unit inside its level
+      uint32_t level[NWG];    // level of the next unit
+      uint32_t a_parity[NWG]; // parity of the a_ready phase that covers the next unit's level
+      bool a_ok[NWG];         // that phase has already been observed
+#pragma unroll
+      for (int w = 0; w < NWG; ++w) done[w] = in_level[w] = level[w] = a_parity[w] = 0, a_ok[w] = false;
       int remaining = tpc;
       long long idle_since = 0;
       while (remaining > 0) {
@@ -499,30 +505,31 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
 #pragma unroll
         for (int w = 0; w < NWG; ++w) {
           if (w >= tpc || done[w] >= units_per_wg) continue;
-          const int64_t in_level = done[w] % units_per_level;
-          const int level = static_cast<int>((done[w] / units_per_level) % a.n_levels);
-          const int64_t level_seq = done[w] / units_per_level;   // how many levels of this warpgroup are behind us
-          bool ok = true;
-          if (in_level == 0 && a_seen[w] == level_seq)
-            ok = ptx::mbar_try_wait(ptx::smem_u32(&bar_a_ready[w]), static_cast<uint32_t>(level_seq & 1));
-          ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-          if (!ok) continue;
-          if (in_level == 0 && a_seen[w] == level_seq) a_seen[w]++;
-          ok = ptx::mbar_try_wait(ptx::smem_u32(&bar_acc_empty[w]), static_cast<uint32_t>((done[w] & 1) ^ 1));
-          ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-          if (!ok) continue;
+          if (!a_ok[w]) {
+            // lane 0 decides for the warp: the 32 probes are not guaranteed to see the same barrier state
+            if (!__shfl_sync(0xffffffffu, ptx::mbar_test_wait(ptx::smem_u32(&bar_a_ready[w]), a_parity[w]) ? 1 : 0, 0)) continue;
+            a_ok[w] = true;
+          }
+          if (!__shfl_sync(0xffffffffu, ptx::mbar_test_wait(ptx::smem_u32(&bar_acc_empty[w]), (done[w] & 1) ^ 1) ? 1 : 0, 0))
+            continue;
           ptx::tc_fence_after_sync();
           if (lane == 0) {
-            const int t = static_cast<int>(in_level / units_per_tile), u = static_cast<int>(in_level % units_per_tile);
+            const int t = in_level[w] / units_per_tile, u = in_level[w] % units_per_tile;
             const int col0 = u * R::kAccCols;
             const int ncols = min(R::kAccCols, p.ntile - col0);
             const uint32_t a_hi = ptx::smem_u32(s_a + w * p.a_bytes);
             issue_unit<D>(tmem_base + w * R::kAccCols, a_hi, a_hi + p.a_bytes / 2, ones,
-                          ptx::smem_u32(s_b + static_cast<size_t>(level * p.n_ktiles + t) * p.tile_bytes), p.ntile, col0, ncols,
-                          ptx::smem_u32(&bar_acc_full[w]));
+                          ptx::smem_u32(s_b + static_cast<size_t>(level[w] * p.n_ktiles + t) * p.tile_bytes), p.ntile, col0,
+                          ncols, ptx::smem_u32(&bar_acc_full[w]));
           }
           __syncwarp();
           done[w]++;
+          if (++in_level[w] == static_cast<uint32_t>(units_per_level)) {  // next unit opens a new level: new residual
+            in_level[w] = 0;
+            level[w] = level[w] + 1 == static_cast<uint32_t>(a.n_levels) ? 0 : level[w] + 1;
+            a_parity[w] ^= 1;
+            a_ok[w] = false;
+          }
           if (done[w] >= units_per_wg) remaining--;
           progressed = true;
         }

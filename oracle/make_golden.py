@@ -185,6 +185,9 @@ def make_hrqvae_forward_cases(ref):
                              use_focal_loss=True, focal_loss_params={"gamma": 2.7, "alpha": 0.24}, dropout_rate=0.0,
                              sem_id_uniqueness_weight=1.5, sem_id_uniqueness_margin=0.0)
             model.tag_prediction_loss.use_mixup = False
+            for m in model.modules():       # TagPredictor adds 0.075 * layer_idx of dropout even at dropout_rate 0
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
             with torch.no_grad():
                 model.layers[1].embedding.weight.mul_(0.3).sub_(0.15)
                 model.layers[2].embedding.weight.mul_(0.12).sub_(0.06)

@@ -84,6 +84,9 @@ def _load_reference_model(mods, g, tag, mname):
                         focal_loss_params={"gamma": 2.7, "alpha": 0.24}, dropout_rate=0.0,
                         sem_id_uniqueness_weight=1.5, sem_id_uniqueness_margin=0.0)
     model.tag_prediction_loss.use_mixup = False
+    for m in model.modules():               # same as the recording run: no dropout noise in the training-mode case
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
     prefix = f"{tag}/state/"
     state = {k[len(prefix):]: t(g[k]) for k in g.files if k.startswith(prefix)}
     missing, unexpected = model.load_state_dict(state, strict=True), None   # the reference's keys, unchanged
@@ -194,7 +197,13 @@ def test_lazy_kmeans_init_in_model(mods):
     assert all(l.kmeans_initted for l in model.layers) and model._can_fuse()
     # after k-means every code of level 0 is used and the loss is far below that of the uniform(0,1) init
     assert torch.unique(q.sem_ids[:, 0]).numel() == 32
-    assert float(q.quantize_loss.mean()) < 1.0
+    fresh = mods.HRqVae(input_dim=64, embed_dim=16, hidden_dims=[32], codebook_size=32, codebook_kmeans_init=False,
+                        codebook_normalize=True, codebook_mode=mods.QuantizeForwardMode.STE, n_layers=2,
+                        n_cat_features=0, tag_class_counts=[3, 4], tag_embed_dim=8).cuda()
+    fresh.encoder.load_state_dict(model.encoder.state_dict())
+    with torch.no_grad():
+        q0 = fresh.get_semantic_ids(fresh.encode(x))
+    assert float(q.quantize_loss.mean()) < 0.5 * float(q0.quantize_loss.mean())   # k-means beats the uniform(0,1) init
 
 
 def test_tokenizer_precompute_corpus_ids(mods, golden_dir):
