@@ -12,6 +12,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of the (converged) warp: ptxas knows that a region guarded by elect.sync has a single active thread, so
+// operands that must live in uniform registers (tcgen05.mma descriptors) need no per-value "waterfall" loop --
+// unlike a region guarded by `lane == 0`.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier --------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -53,6 +68,27 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// ---- shared-memory progress counters (cheap to poll: one LDS instead of a ~150-cycle mbarrier probe) -----------
+__device__ __forceinline__ void counter_add_release(uint32_t addr, uint32_t v) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t counter_ld_acquire(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+// bounded spin until the counter reaches `need` (wrap-safe comparison)
+__device__ __forceinline__ void counter_wait(uint32_t addr, uint32_t need) {
+  if (static_cast<int32_t>(counter_ld_acquire(addr) - need) >= 0) return;
+  const long long t0 = clock64();
+  while (static_cast<int32_t>(counter_ld_acquire(addr) - need) < 0) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("hidvae_b200: counter wait timed out (block %d thread %d addr 0x%x need %u)\n", blockIdx.x, threadIdx.x, addr, need);
+      __trap();
+    }
+  }
+}
+
 // Bounded wait: a protocol bug must end the kernel with an error, never hang the GPU (a hung box is a lost box).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -158,6 +194,15 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= 1ull << 46;
   return d;
+}
+// The same descriptor split in its two 32-bit words, so that the issuing thread only adds to the low word:
+//   lo = (addr >> 4) | (LBO >> 4) << 16,  hi = (SBO >> 4) | version 1 at bit 46 (bit 14 of the high word)
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 // Instruction descriptor for kind::f16: fp32 accumulate (bits [4,6) = 1), A/B = bf16 (bits [7,10), [10,13) = 1),
 // both K-major (bits 15, 16 = 0), N>>3 at [17,23), M>>4 at [24,29).

@@ -19,6 +19,8 @@
 //   hands it whole rows, the running (max, argmax) stays in registers, then the warp gathers the fp32 code rows,
 //   forms emb_out / loss / the next residual in registers and re-stages the residual (bf16 hi/lo) as the next
 //   level's A operand.  The [N, K] score matrix never leaves the SM.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -69,8 +71,14 @@ bool plan_for(int d, int k, int n_levels, int n_wg, TcPlan* p) {
 // The packed image (ntile, tile_bytes) does not depend on n_wg, so pack and forward always agree.
 bool make_plan(int d, int k, int n_levels, TcPlan* p) {
   if (d % 16 != 0 || d < 16 || d > 128 || k < 1 || n_levels < 1) return false;
-  // four tiles in flight when the whole operand image stays resident beside four A buffers; else two
-  if (plan_for(d, k, n_levels, 4, p) && p->resident) return true;
+  // four tiles in flight when the whole operand image stays resident beside four A buffers; else two.
+  // HIDVAE_TC_NWG=2|4 overrides the choice (tuning experiments only).
+  static const int forced = [] {
+    const char* e = getenv("HIDVAE_TC_NWG");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (forced == 2) return plan_for(d, k, n_levels, 2, p);
+  if (plan_for(d, k, n_levels, 4, p) && (p->resident || forced == 4)) return true;
   return plan_for(d, k, n_levels, 2, p);
 }
 
@@ -283,33 +291,32 @@ struct Roles {
   static constexpr int kAccCols = kTmemCols / NWG;  // fp32 accumulator columns of one warpgroup
 };
 
-// issue the 3*D/16 + 1 MMAs of one unit (`ncols` codes starting at code `col0` of the staged N tile)
+// issue the 3*D/16 + 1 MMAs of one unit (`ncols` codes starting at code `col0` of the staged N tile).
+// Called by ONE elected thread.  Descriptors are assembled from 32-bit words so that stepping through K chunks is
+// one add per operand (address field in 16-byte units: A chunk = 128 rows x 16 B = 128 units, B chunk = ntile).
 template <int D>
 __device__ __forceinline__ void issue_unit(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t ones, uint32_t b_tile,
                                            int ntile, int col0, int ncols, uint32_t bar_full) {
   const uint32_t idesc = ptx::umma_idesc_bf16(kTileRows, ncols);
-  const uint32_t chunk_b = ntile * 16;      // bytes between K chunks of the B image
-  const uint32_t chunk_a = kTileRows * 16;  // bytes between K chunks of the A operand
+  const uint32_t hi = ptx::umma_desc_hi(128);
+  const uint32_t chunk_b = ntile * 16;                            // bytes between K chunks of the B image
+  const uint32_t a_step = 2 * kTileRows, b_step = 2 * ntile;     // one K=16 step = two chunks, in 16-byte units
+  const uint32_t d_ahi = ptx::umma_desc_lo(a_hi, kTileRows * 16), d_alo = ptx::umma_desc_lo(a_lo, kTileRows * 16);
+  const uint32_t d_one = ptx::umma_desc_lo(ones, kTileRows * 16);
   const uint32_t b_hi = b_tile + col0 * 16;
-  const uint32_t b_lo = b_hi + (D / 8) * chunk_b;
-  const uint32_t b_nrm = b_lo + (D / 8) * chunk_b;
-  uint32_t accumulate = 0;
+  const uint32_t d_bhi = ptx::umma_desc_lo(b_hi, chunk_b);
+  const uint32_t d_blo = ptx::umma_desc_lo(b_hi + (D / 8) * chunk_b, chunk_b);
+  const uint32_t d_bnrm = ptx::umma_desc_lo(b_hi + 2 * (D / 8) * chunk_b, chunk_b);
 #pragma unroll
-  for (int j = 0; j < D / 16; ++j) {  // r_hi . c_hi
-    ptx::umma_bf16(acc, ptx::umma_smem_desc(a_hi + j * 2 * chunk_a, chunk_a, 128),
-                   ptx::umma_smem_desc(b_hi + j * 2 * chunk_b, chunk_b, 128), idesc, accumulate);
-    accumulate = 1;
-  }
+  for (int j = 0; j < D / 16; ++j)  // r_hi . c_hi
+    ptx::umma_bf16(acc, ptx::umma_desc(d_ahi + j * a_step, hi), ptx::umma_desc(d_bhi + j * b_step, hi), idesc, j > 0 ? 1u : 0u);
 #pragma unroll
   for (int j = 0; j < D / 16; ++j)  // r_lo . c_hi
-    ptx::umma_bf16(acc, ptx::umma_smem_desc(a_lo + j * 2 * chunk_a, chunk_a, 128),
-                   ptx::umma_smem_desc(b_hi + j * 2 * chunk_b, chunk_b, 128), idesc, 1);
+    ptx::umma_bf16(acc, ptx::umma_desc(d_alo + j * a_step, hi), ptx::umma_desc(d_bhi + j * b_step, hi), idesc, 1u);
 #pragma unroll
   for (int j = 0; j < D / 16; ++j)  // r_hi . c_lo
-    ptx::umma_bf16(acc, ptx::umma_smem_desc(a_hi + j * 2 * chunk_a, chunk_a, 128),
-                   ptx::umma_smem_desc(b_lo + j * 2 * chunk_b, chunk_b, 128), idesc, 1);
-  // 1 * (-|c|^2 / 2)
-  ptx::umma_bf16(acc, ptx::umma_smem_desc(ones, chunk_a, 128), ptx::umma_smem_desc(b_nrm, chunk_b, 128), idesc, 1);
+    ptx::umma_bf16(acc, ptx::umma_desc(d_ahi + j * a_step, hi), ptx::umma_desc(d_blo + j * b_step, hi), idesc, 1u);
+  ptx::umma_bf16(acc, ptx::umma_desc(d_one, hi), ptx::umma_desc(d_bnrm, hi), idesc, 1u);  // 1 * (-|c|^2 / 2)
   ptx::umma_commit(bar_full);
 }
 
@@ -325,10 +332,12 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
 
   uint64_t* bar_b_full = s_bar;                       // [kMaxStages]
   uint64_t* bar_b_empty = s_bar + kMaxStages;         // [kMaxStages]
-  uint64_t* bar_a_ready = s_bar + 2 * kMaxStages;     // [kMaxWg]
-  uint64_t* bar_acc_full = bar_a_ready + kMaxWg;      // [kMaxWg]
-  uint64_t* bar_acc_empty = bar_acc_full + kMaxWg;    // [kMaxWg]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + kMaxWg);
+  uint64_t* bar_acc_full = s_bar + 2 * kMaxStages;    // [kMaxWg]  MMA -> epilogue (tcgen05.commit needs an mbarrier)
+  // epilogue -> MMA issuer progress counters, polled by ONE thread: a plain LDS answers in ~30 cycles where an
+  // mbarrier probe takes ~150, and the issuer has up to 2 x NWG conditions to watch
+  uint32_t* cnt_a_ready = reinterpret_cast<uint32_t*>(bar_acc_full + kMaxWg);  // [kMaxWg] warp arrivals: 4 per staged level
+  uint32_t* cnt_acc_empty = cnt_a_ready + kMaxWg;                              // [kMaxWg] warp arrivals: 4 per drained unit
+  uint32_t* s_tmem = cnt_acc_empty + kMaxWg;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -339,9 +348,9 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
       ptx::mbar_init(ptx::smem_u32(&bar_b_empty[s]), 1);
     }
     for (int w = 0; w < kMaxWg; ++w) {
-      ptx::mbar_init(ptx::smem_u32(&bar_a_ready[w]), 4);
       ptx::mbar_init(ptx::smem_u32(&bar_acc_full[w]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bar_acc_empty[w]), 4);
+      cnt_a_ready[w] = 0;
+      cnt_acc_empty[w] = 0;
     }
     ptx::fence_mbar_init();
   }
@@ -377,9 +386,9 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
     uint8_t* a_hi = s_a + w * p.a_bytes;
     uint8_t* a_lo = a_hi + p.a_bytes / 2;
     const uint32_t acc_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + w * R::kAccCols;
-    const uint32_t bar_ready = ptx::smem_u32(&bar_a_ready[w]);
+    const uint32_t cnt_ready = ptx::smem_u32(&cnt_a_ready[w]);
     const uint32_t bar_full = ptx::smem_u32(&bar_acc_full[w]);
-    const uint32_t bar_empty = ptx::smem_u32(&bar_acc_empty[w]);
+    const uint32_t cnt_empty = ptx::smem_u32(&cnt_acc_empty[w]);
     uint32_t acc_phase = 0;
     const uint32_t scratch = ptx::smem_u32(a_hi);   // transpose scratch = this warpgroup's A buffer (see above)
     const int row0 = quarter * 32;                  // first tile row of this warp
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
         stage_a_operand<D>(a_hi, a_lo, row_in_tile, r);
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_ready);
+        if (lane == 0) ptx::counter_add_release(cnt_ready, 1);
 
         float best = -INFINITY;
         int best_k = 0;
@@ -420,7 +429,7 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
             }
             ptx::tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bar_empty);
+            if (lane == 0) ptx::counter_add_release(cnt_empty, 1);
           }
         }
         best_k = min(best_k, a.k - 1);
@@ -490,63 +499,63 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
                                     ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
       const int units_per_level = p.n_ktiles * units_per_tile;
       const uint32_t units_per_wg = static_cast<uint32_t>(my_groups * a.n_levels * units_per_level);
-      // per-warpgroup progress, kept in registers (the loops over w are fully unrolled)
-      uint32_t done[NWG];     // units issued so far
-      uint32_t in_level[NWG]; // position of the next unit inside its level
-      uint32_t level[NWG];    // level of the next unit
-      uint32_t a_parity[NWG]; // parity of the a_ready phase that covers the next unit's level
-      bool a_ok[NWG];         // that phase has already been observed
+      {
+        // The whole warp runs the scheduler with warp-uniform state (lane 0's view of the counters decides); the
+        // MMAs and the commit are issued by one elected lane.
+        uint32_t done[NWG];         // units issued so far
+        uint32_t in_level[NWG];     // position of the next unit inside its level
+        uint32_t level[NWG];        // level of the next unit
+        uint32_t levels_seen[NWG];  // number of staged residuals already consumed
 #pragma unroll
-      for (int w = 0; w < NWG; ++w) done[w] = in_level[w] = level[w] = a_parity[w] = 0, a_ok[w] = false;
-      int remaining = tpc;
-      long long idle_since = 0;
-      while (remaining > 0) {
-        bool progressed = false;
+        for (int w = 0; w < NWG; ++w) done[w] = in_level[w] = level[w] = levels_seen[w] = 0;
+        int remaining = tpc;
+        long long idle_since = 0;
+        while (remaining > 0) {
+          bool progressed = false;
 #pragma unroll
-        for (int w = 0; w < NWG; ++w) {
-          if (w >= tpc || done[w] >= units_per_wg) continue;
-          if (!a_ok[w]) {
-            // lane 0 decides for the warp: the 32 probes are not guaranteed to see the same barrier state
-            if (!__shfl_sync(0xffffffffu, ptx::mbar_test_wait(ptx::smem_u32(&bar_a_ready[w]), a_parity[w]) ? 1 : 0, 0)) continue;
-            a_ok[w] = true;
+          for (int w = 0; w < NWG; ++w) {
+            if (w >= tpc || done[w] >= units_per_wg) continue;
+            // residual of this unit's level staged by all 4 warps?  accumulator drained of every earlier unit?
+            const uint32_t ready = __shfl_sync(0xffffffffu, ptx::counter_ld_acquire(ptx::smem_u32(&cnt_a_ready[w])), 0);
+            if (static_cast<int32_t>(ready - 4 * (levels_seen[w] + 1)) < 0) continue;
+            const uint32_t drained = __shfl_sync(0xffffffffu, ptx::counter_ld_acquire(ptx::smem_u32(&cnt_acc_empty[w])), 0);
+            if (static_cast<int32_t>(drained - 4 * done[w]) < 0) continue;
+            ptx::tc_fence_after_sync();
+            if (ptx::elect_one()) {
+              const int t = in_level[w] / units_per_tile, u = in_level[w] % units_per_tile;
+              const int col0 = u * R::kAccCols;
+              const int ncols = min(R::kAccCols, p.ntile - col0);
+              const uint32_t a_hi = ptx::smem_u32(s_a + w * p.a_bytes);
+              issue_unit<D>(tmem_base + w * R::kAccCols, a_hi, a_hi + p.a_bytes / 2, ones,
+                            ptx::smem_u32(s_b + static_cast<size_t>(level[w] * p.n_ktiles + t) * p.tile_bytes), p.ntile, col0,
+                            ncols, ptx::smem_u32(&bar_acc_full[w]));
+            }
+            __syncwarp();
+            done[w]++;
+            if (++in_level[w] == static_cast<uint32_t>(units_per_level)) {  // next unit opens a new level
+              in_level[w] = 0;
+              level[w] = level[w] + 1 == static_cast<uint32_t>(a.n_levels) ? 0 : level[w] + 1;
+              levels_seen[w]++;
+            }
+            if (done[w] >= units_per_wg) remaining--;
+            progressed = true;
           }
-          if (!__shfl_sync(0xffffffffu, ptx::mbar_test_wait(ptx::smem_u32(&bar_acc_empty[w]), (done[w] & 1) ^ 1) ? 1 : 0, 0))
-            continue;
-          ptx::tc_fence_after_sync();
-          if (lane == 0) {
-            const int t = in_level[w] / units_per_tile, u = in_level[w] % units_per_tile;
-            const int col0 = u * R::kAccCols;
-            const int ncols = min(R::kAccCols, p.ntile - col0);
-            const uint32_t a_hi = ptx::smem_u32(s_a + w * p.a_bytes);
-            issue_unit<D>(tmem_base + w * R::kAccCols, a_hi, a_hi + p.a_bytes / 2, ones,
-                          ptx::smem_u32(s_b + static_cast<size_t>(level[w] * p.n_ktiles + t) * p.tile_bytes), p.ntile, col0,
-                          ncols, ptx::smem_u32(&bar_acc_full[w]));
-          }
-          __syncwarp();
-          done[w]++;
-          if (++in_level[w] == static_cast<uint32_t>(units_per_level)) {  // next unit opens a new level: new residual
-            in_level[w] = 0;
-            level[w] = level[w] + 1 == static_cast<uint32_t>(a.n_levels) ? 0 : level[w] + 1;
-            a_parity[w] ^= 1;
-            a_ok[w] = false;
-          }
-          if (done[w] >= units_per_wg) remaining--;
-          progressed = true;
-        }
-        if (progressed) {
-          idle_since = 0;
-        } else {
-          if (idle_since == 0) idle_since = clock64();
-          if (clock64() - idle_since > 4000000000LL) {
-            if (lane == 0) printf("hidvae_b200: MMA scheduler starved (block %d)\n", blockIdx.x);
-            __trap();
+          if (progressed) {
+            idle_since = 0;
+          } else {
+            if (idle_since == 0) idle_since = clock64();
+            if (clock64() - idle_since > 4000000000LL) {
+              if (lane == 0) printf("hidvae_b200: MMA scheduler starved (block %d)\n", blockIdx.x);
+              __trap();
+            }
           }
         }
       }
+      __syncwarp();
     } else {
       // Streamed operand images: all warpgroups consume the same stage in lock step (one load serves tpc tiles).
       uint32_t it = 0;
-      uint32_t a_phase[kMaxWg] = {0, 0, 0, 0};
+      uint32_t levels_seen[kMaxWg] = {0, 0, 0, 0};
       uint32_t acc_uses[kMaxWg] = {0, 0, 0, 0};
       for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         for (int tile = 0; tile < total_tiles; ++tile, ++it) {
@@ -556,14 +565,14 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
           const uint32_t b_tile = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
           for (int w = 0; w < tpc; ++w) {
             if (t == 0) {
-              ptx::mbar_wait(ptx::smem_u32(&bar_a_ready[w]), a_phase[w]);
-              a_phase[w] ^= 1;
+              levels_seen[w]++;
+              ptx::counter_wait(ptx::smem_u32(&cnt_a_ready[w]), 4 * levels_seen[w]);
             }
             for (int u = 0; u < units_per_tile; ++u) {
-              ptx::mbar_wait(ptx::smem_u32(&bar_acc_empty[w]), (acc_uses[w] & 1) ^ 1);
+              ptx::counter_wait(ptx::smem_u32(&cnt_acc_empty[w]), 4 * acc_uses[w]);
               acc_uses[w]++;
               ptx::tc_fence_after_sync();
-              if (lane == 0) {
+              if (ptx::elect_one()) {
                 const int col0 = u * R::kAccCols;
                 const uint32_t a_hi = ptx::smem_u32(s_a + w * p.a_bytes);
                 issue_unit<D>(tmem_base + w * R::kAccCols, a_hi, a_hi + p.a_bytes / 2, ones, b_tile, p.ntile, col0,
@@ -572,7 +581,7 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
               __syncwarp();
             }
           }
-          if (lane == 0) ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
+          if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
           __syncwarp();
         }
       }
