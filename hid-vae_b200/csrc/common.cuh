@@ -55,6 +55,8 @@ int launch_rq_fwd_tc(const RqFwdArgs& a, int d, bool rot, void* workspace, size_
                      cudaStream_t stream);
 int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* workspace, size_t workspace_bytes,
                    cudaStream_t stream);
+// previous kernel generation, A/B runs only (HIDVAE_TC_IMPL=v4); `packed` = image written by launch_rq_pack
+int launch_rq_fwd_tc_v4(const RqFwdArgs& a, int d, bool rot, void* packed, cudaStream_t stream);
 bool rq_fwd_tc_supported(int d, int k, int n_levels);
 size_t rq_fwd_tc_workspace_bytes(int d, int k, int n_levels);
 

@@ -114,6 +114,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
                : "memory");
 }
 
+// ---- named barriers among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads) ---------------------------
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// ask L2 to fetch `bytes` (multiple of 16) starting at the 16-byte aligned global address (SASS: UBLKPF)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 // ---- register reallocation between warpgroups (all warps of a warpgroup execute it) ------------------------------
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {

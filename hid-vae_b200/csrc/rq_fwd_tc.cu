@@ -1,24 +1,39 @@
-// tcgen05 variant of the fused L-level residual quantiser (HV_ALGO_TCGEN05) for sm_100a.
+// tcgen05 kernel of the fused L-level residual quantiser (HV_ALGO_TCGEN05) for sm_100a -- generation 5.
 //
-// Mapping (re-derived for B200 and revised after the first ncu captures, profiles/):
-//   GEMM  M = 128 rows of one row tile (= the 128 TMEM lanes), N = up to 256 codes, reduction = D.
-//   score[row, k] = r.c_k - |c_k|^2 / 2   (argmax == argmin of |r|^2 + |c_k|^2 - 2 r.c_k; |r|^2 is row-constant)
-//   fp32-grade scores from bf16 tensor cores: r = r_hi + r_lo, c = c_hi + c_lo (bf16 each), three products
-//   r_hi.c_hi + r_lo.c_hi + r_hi.c_lo accumulated in the fp32 TMEM accumulator, and -|c|^2/2 folded in as one
-//   more K=16 step (A = [1,1,1,0..], B = the norm split in three bf16 pieces).  3*D/16 + 1 tcgen05.mma per unit.
-//   The codebooks are pre-packed once (hv_rq_pack_codebooks) into the UMMA K-major core-matrix layout and staged
-//   by 1-D bulk TMA copies: resident in shared memory for all L levels when they fit (K=256, D=32, L=3: 120 KB),
-//   otherwise streamed through a ring of stages (K=4096, D=64).
+// What one (row tile, level) costs, measured on the previous generation (profiles/README.md): 7 tcgen05.mma of
+// N = 256 (896 tensor cycles) against ~6200 warp instructions of epilogue (1550 issue cycles per SM sub-partition),
+// and the epilogue warps spent a third of their time waiting for the accumulator.  This generation is built
+// around those two numbers:
 //
-//   A row's L levels are a strictly serial chain (stage A -> MMA -> argmax scan -> code gather -> residual), each
-//   link latency-bound, so throughput comes from the NUMBER OF ROW TILES IN FLIGHT per SM: the persistent CTA runs
-//   NWG epilogue warpgroups (4 where shared memory allows, else 2), each owning one 128-row tile and one
-//   512/NWG-column fp32 accumulator in TMEM; a level's N tile is processed in units of at most that many columns.
-//   One more warp is the TMA producer, one allocates TMEM and issues every tcgen05.mma, serving whichever
-//   warpgroup is ready first.  Epilogue thread t owns row t of its tile for all L levels: tcgen05.ld (32x32b)
-//   hands it whole rows, the running (max, argmax) stays in registers, then the warp gathers the fp32 code rows,
-//   forms emb_out / loss / the next residual in registers and re-stages the residual (bf16 hi/lo) as the next
-//   level's A operand.  The [N, K] score matrix never leaves the SM.
+//   GEMM      M = 128 rows of a row tile (the 128 TMEM lanes), N = 256 codes (one operand image), reduction = D.
+//             score[row, k] = r.c_k - |c_k|^2 / 2 (argmax == the reference's argmin, modules/quantize.py:108-122),
+//             fp32-grade from bf16 tensor cores: r = r_hi + r_lo, c = c_hi + c_lo, products hi.hi + lo.hi + hi.lo and
+//             the norm term (three bf16 pieces against a constant-ones A block) accumulate in fp32 TMEM:
+//             3*D/16 + 1 tcgen05.mma (M128 N128 K16) per 128-code unit, two units per image.
+//   SLOTS     the persistent CTA (one per SM) keeps TWO row tiles in flight ("slots"), each with a 256-column
+//             accumulator (2 x 256 = the 512 TMEM columns) and EIGHT warps.  The slot issues its own MMAs (one
+//             elected thread, straight after the slot-wide barrier that follows the A-operand staging; there is no
+//             scheduler warp to poll), both units back to back with one tcgen05.commit each, so the scan of unit 0
+//             overlaps the MMAs of unit 1 and the other slot's epilogue overlaps this slot's MMAs.
+//   SCAN      thread (quarter q, half h, lane) owns accumulator row 32q + lane and 64 columns of each unit (four
+//             32-column chunks, tcgen05.ld 32x32b).  Instead of an argmax per chunk it folds the chunks into 32
+//             running column classes  g_j = max_c f[c][j]  (one FMNMX per score) and keeps the four chunk maxima
+//             (3-ary FMNMX3 tree); the row maximum m is the largest chunk maximum, the chunk is the one whose maximum
+//             equals m and the class is found on the FMA pipe:  sum_j sat((g_j - m) * 2^120 + 1) * (64 + j)  is
+//             64 + j* when exactly one class attains m.  ~1.1 ALU-pipe and 0.8 FMA-pipe instructions per score
+//             instead of 3.4.  If more than one class or chunk attains m (duplicate code rows, all-zero inputs) the
+//             warp re-reads its chunks and takes the exact first-index path, so exact ties still resolve to the
+//             lowest index like torch.min (modules/quantize.py:122).
+//   ROW WORK  everything that is per row rather than per score (x load, code gather, STE / rotation value, loss,
+//             residual update, bf16 hi/lo split of the next A operand, stores) runs in a row-cooperative layout: a
+//             thread holds one 8-float K chunk of D/16 rows, so global accesses are coalesced 32-byte pieces, the A
+//             operand is written with conflict-free 128-bit stores straight into the UMMA core-matrix layout and a
+//             row costs D/8 lanes x 8 floats instead of one thread x D floats.  The two halves of a row meet through
+//             a 4 KB candidate table in shared memory.
+//   OPERANDS  codebook images are packed once (hv_rq_pack_codebooks) and staged by 1-D bulk TMA copies: resident in
+//             shared memory for all levels when they fit (K = 256, D = 32, L = 3: 120 KB), otherwise streamed through
+//             a ring of stages that both slots consume in lock step (K = 4096, D = 64).
+//   The [N, K] score table never leaves the SM; only ids (and emb_out / loss in training) go to HBM.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -28,36 +43,39 @@ namespace hv {
 namespace {
 
 constexpr int kTileRows = 128;
+constexpr int kNTile = 256;                 // codes per operand image (= accumulator columns of a slot)
+constexpr int kUnitCols = 128;              // N of one tcgen05.mma
+constexpr int kSlots = 2;                   // row tiles in flight per CTA
+constexpr int kSlotWarps = 8;
+constexpr int kSlotThreads = kSlotWarps * 32;
+constexpr int kThreads = kSlots * kSlotThreads;  // 512: the register file gives every thread 128 registers
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 16;
-constexpr int kMaxWg = 4;
-constexpr int kOnesBytes = 2 * kTileRows * 16;  // one K=16 step of the A operand: [2 chunks][128 rows][8 bf16]
+constexpr int kOnesBytes = 2 * kTileRows * 16;              // one K=16 step of the A operand: [2 chunks][128 rows][8 bf16]
+constexpr int kCandBytes = kSlots * 2 * kTileRows * 8;      // (max, column) per slot, half, row
+constexpr int kBarBytes = 1024;
 constexpr int kSmemLimit = 227 * 1024;
 
 struct TcPlan {
-  int ntile;       // codes per N tile (multiple of 32, <= 256)
-  int n_ktiles;    // N tiles per level
-  int tile_bytes;  // packed image of one (level, N tile)
-  int stages;      // shared-memory stages for packed images
-  int resident;    // 1: every (level, tile) image has its own stage and is loaded once
+  int n_ktiles;    // operand images per level
+  int tile_bytes;  // one packed image
+  int stages;      // shared-memory stages for images
+  int resident;    // 1: every (level, image) has its own stage and is loaded once
   int smem_bytes;
-  int a_bytes;     // one warpgroup's A operand (hi + lo) == one fp32 row tile
-  int n_wg;        // epilogue warpgroups = row tiles in flight per CTA
+  int a_bytes;     // one slot's A operand (hi + lo) == one fp32 row tile
 };
 
-bool plan_for(int d, int k, int n_levels, int n_wg, TcPlan* p) {
-  const int kpad = (k + 31) / 32 * 32;
-  p->ntile = kpad <= 256 ? kpad : 256;
-  p->n_ktiles = (k + p->ntile - 1) / p->ntile;
-  p->tile_bytes = p->ntile * (4 * d + 32);
+bool make_plan(int d, int k, int n_levels, TcPlan* p) {
+  if ((d != 16 && d != 32 && d != 64) || k < 1 || n_levels < 1) return false;
+  p->n_ktiles = (k + kNTile - 1) / kNTile;
+  p->tile_bytes = kNTile * (4 * d + 32);
   p->a_bytes = kTileRows * d * 4;
-  p->n_wg = n_wg;
-  const int fixed = n_wg * p->a_bytes + kOnesBytes + 1024;
+  const int fixed = kSlots * p->a_bytes + kOnesBytes + kCandBytes + kBarBytes;
   const int budget = kSmemLimit - fixed;
-  const int total_tiles = n_levels * p->n_ktiles;
-  if (total_tiles <= kMaxStages && static_cast<long long>(total_tiles) * p->tile_bytes <= budget) {
+  const long long total_tiles = static_cast<long long>(n_levels) * p->n_ktiles;
+  if (total_tiles <= kMaxStages && total_tiles * p->tile_bytes <= budget) {
     p->resident = 1;
-    p->stages = total_tiles;
+    p->stages = static_cast<int>(total_tiles);
   } else {
     p->resident = 0;
     p->stages = budget / p->tile_bytes;
@@ -68,38 +86,24 @@ bool plan_for(int d, int k, int n_levels, int n_wg, TcPlan* p) {
   return true;
 }
 
-// The packed image (ntile, tile_bytes) does not depend on n_wg, so pack and forward always agree.
-bool make_plan(int d, int k, int n_levels, TcPlan* p) {
-  if (d % 16 != 0 || d < 16 || d > 128 || k < 1 || n_levels < 1) return false;
-  // four tiles in flight when the whole operand image stays resident beside four A buffers; else two.
-  // HIDVAE_TC_NWG=2|4 overrides the choice (tuning experiments only).
-  static const int forced = [] {
-    const char* e = getenv("HIDVAE_TC_NWG");
-    return e != nullptr ? atoi(e) : 0;
-  }();
-  if (forced == 2) return plan_for(d, k, n_levels, 2, p);
-  if (plan_for(d, k, n_levels, 4, p) && (p->resident || forced == 4)) return true;
-  return plan_for(d, k, n_levels, 2, p);
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// Pack kernel: fp32 [L, K, D] -> per (level, N tile) image
-//   [c_hi : D/8 chunks][c_lo : D/8 chunks][norm : 2 chunks], chunk = [ntile codes][8 bf16] (16 B per code)
+// Pack kernel: fp32 [L, K, D] -> per (level, 256-code image)
+//   [c_hi : D/8 chunks][c_lo : D/8 chunks][norm : 2 chunks], chunk = [256 codes][8 bf16] (16 B per code)
 // Padded codes (index >= K) get zero vectors and a -1e30 norm term so they can never win the argmax.
 // ---------------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void rq_pack_codebooks_kernel(const float* __restrict__ codebooks, int n_levels, int k, int ntile,
-                                         int n_ktiles, int tile_bytes, uint8_t* __restrict__ packed) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (level, tile, code in tile)
-  const int total = n_levels * n_ktiles * ntile;
+__global__ void rq_pack_codebooks_kernel(const float* __restrict__ codebooks, int n_levels, int k, int n_ktiles,
+                                         int tile_bytes, uint8_t* __restrict__ packed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (level, image, code in image)
+  const int total = n_levels * n_ktiles * kNTile;
   if (idx >= total) return;
-  const int c = idx % ntile;
-  const int tile = idx / ntile;  // level * n_ktiles + t
+  const int c = idx % kNTile;
+  const int tile = idx / kNTile;  // level * n_ktiles + t
   const int t = tile % n_ktiles;
   const int level = tile / n_ktiles;
-  const int code = t * ntile + c;
+  const int code = t * kNTile + c;
   uint8_t* img = packed + static_cast<size_t>(tile) * tile_bytes;
-  const size_t chunk_stride = static_cast<size_t>(ntile) * 16;
+  constexpr size_t chunk_stride = static_cast<size_t>(kNTile) * 16;
   uint8_t* hi_base = img;
   uint8_t* lo_base = img + (D / 8) * chunk_stride;
   uint8_t* nrm_base = img + 2 * (D / 8) * chunk_stride;
@@ -142,33 +146,55 @@ __global__ void rq_pack_codebooks_kernel(const float* __restrict__ codebooks, in
 
 struct TcParams {
   const uint8_t* packed;
-  int ntile;
   int n_ktiles;
   int tile_bytes;
   int stages;
   int resident;
   int a_bytes;
-  int tiles_per_cta;  // active warpgroups (1..NWG): fewer when there are not enough row tiles to fill the SMs
+  int tiles_per_cta;  // active slots (1 or 2): one when there are not enough row tiles to give every SM two
 };
 
-// bf16 hi/lo split of one row into the K-major core-matrix layout: chunk kc of row `row` lives at
-// base + kc * (128 rows * 16 B) + row * 16.
+// ---------------------------------------------------------------------------------------------------------
+// Row-cooperative layout: the 256 threads of a slot hold the slot's 128 x D fp32 rows as 8-float K chunks.
+//   lane -> (j = lane % RPI, kc = lane / RPI);  warp wt owns rows [16 wt, 16 wt + 16);  the thread's g-th row is
+//   16 wt + g * RPI + j.  A quarter warp (8 consecutive lanes) then shares kc and covers 8 consecutive rows, which
+//   makes the 128-bit stores into the core-matrix layout (chunk kc of row `row` at kc * 2048 + row * 16) conflict free.
+// ---------------------------------------------------------------------------------------------------------
 template <int D>
-__device__ __forceinline__ void stage_a_operand(uint8_t* a_hi, uint8_t* a_lo, int row, const float (&r)[D]) {
+struct Rc {
+  static constexpr int KC = D / 8;     // 16-byte (8 x bf16) K chunks per row == lanes per row
+  static constexpr int RPI = 32 / KC;  // rows per warp instruction
+  static constexpr int RPT = KC / 2;   // rows per thread
+  static_assert(KC >= 2 && KC <= 8 && RPI * RPT == 16, "row-cooperative layout covers 16 rows per warp");
+};
+
+// sum over the KC lanes that share a row (they differ in the lane bits above log2(RPI))
+template <int D>
+__device__ __forceinline__ float row_sum(float v) {
 #pragma unroll
-  for (int kc = 0; kc < D / 8; ++kc) {
-    uint32_t hi[4], lo[4];
+  for (int m = Rc<D>::RPI; m < 32; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+// bf16 hi/lo split of 8 consecutive floats -> one 16-byte chunk entry each of the hi and the lo operand
+__device__ __forceinline__ void split8(const float (&r)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float x0 = r[kc * 8 + 2 * j], x1 = r[kc * 8 + 2 * j + 1];
-      const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-      const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - __low2float(h), x1 - __high2float(h));
-      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
-    }
-    *reinterpret_cast<uint4*>(a_hi + kc * (kTileRows * 16) + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(a_lo + kc * (kTileRows * 16) + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  for (int j = 0; j < 4; ++j) {
+    const float x0 = r[2 * j], x1 = r[2 * j + 1];
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+    const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hh);
+    const float h0 = __uint_as_float(hw << 16), h1 = __uint_as_float(hw & 0xFFFF0000u);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+    h[j] = hw;
+    l[j] = *reinterpret_cast<const uint32_t*>(&ll);
   }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
@@ -177,130 +203,44 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return d;
 }
 
-// max of 32 floats as a 3-ary tree: 17 independent-ish FMNMX3 instead of a 32-long dependent compare/select chain
-__device__ __forceinline__ float max32(const float (&f)[32]) {
+// max of 32 floats as a 3-ary tree: 17 FMNMX3/FMNMX instead of a 32-long dependent chain
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
   float a[11];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) a[i] = max3(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
-  a[10] = fmaxf(f[30], f[31]);
+  for (int i = 0; i < 10; ++i)
+    a[i] = max3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+  a[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
   const float b0 = max3(a[0], a[1], a[2]), b1 = max3(a[3], a[4], a[5]), b2 = max3(a[6], a[7], a[8]);
   const float b3 = fmaxf(a[9], a[10]);
   return fmaxf(max3(b0, b1, b2), b3);
 }
 
-// Running (max, argmax) over one 32-column chunk of scores held in registers; the first (lowest) index wins exact
-// ties, like torch.min on the distances (modules/quantize.py:122).
-//   phase A  m = max of the chunk (FMNMX3 tree, ALU pipe)
-//   phase B  only if some row of the warp improves: position of the first element equal to m, computed on the FMA
-//            pipe so it does not compete with phase A:  t_j = (f_j - m) * 2^120 + (32 - j)  is (32 - j) where
-//            f_j == m and hugely negative elsewhere; the max of t_j therefore names the first maximiser.
-//            (exact for any two scores that differ by at least 2^-114.)  t overwrites f: no extra registers.
-__device__ __forceinline__ void scan_chunk(uint32_t (&v)[32], int base, float& best, int& best_k) {
-  float f[32];
+constexpr float kBig = 1.329227995784916e36f;  // 2^120
+
+// Exact first-index (max, argmax) of one 32-column chunk against the running pair -- the slow path, taken only by
+// warps in which some row has more than one maximiser.  t_j = (f_j - m) * 2^120 + (32 - j) is 32 - j where f_j == m
+// and hugely negative elsewhere, so its maximum names the first maximiser.
+__device__ __forceinline__ void scan_chunk_exact(const uint32_t (&v)[32], int base, float& best, int& best_col) {
+  const float m = max32(v);
+  if (m > best) {  // strict: an earlier chunk keeps exact ties
+    float t = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-  const float m = max32(f);
-  const bool better = m > best;  // strict: an earlier chunk keeps exact ties
-  if (__any_sync(0xffffffffu, better)) {
-    const float kBig = 1.329227995784916e36f;  // 2^120
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j] - m, kBig, static_cast<float>(32 - j));
-    const int loc = 32 - static_cast<int>(max32(f));
-    if (better) {
-      best = m;
-      best_k = base + loc;
-    }
+    for (int j = 0; j < 32; ++j) t = fmaxf(t, fmaf(__uint_as_float(v[j]) - m, kBig, static_cast<float>(32 - j)));
+    best = m;
+    best_col = base + 32 - static_cast<int>(t);
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Warp-cooperative row movers.  One thread owns one row (D fp32 = D/4 16-byte units), but a warp-wide 128-bit
-// access in which every lane touches a different row costs 32 L1 wavefronts; so rows travel between global memory
-// and their owner threads through a swizzled transpose in shared memory: global side = each row handled by D/4
-// adjacent lanes (4 wavefronts per instruction at D = 32), owner side = conflict-free 128-bit shared accesses.
-// The scratch is the warpgroup's own A-operand buffer (128 rows x D x 4 bytes), free whenever no MMA is reading
-// it; warp q only touches the slots of its rows [32q, 32q+32), so __syncwarp is the only synchronisation.
-// ---------------------------------------------------------------------------------------------------------
-template <int D>
-__device__ __forceinline__ uint32_t xpose_addr(uint32_t base, int row, int u) {
-  return base + u * (kTileRows * 16) + ((row & ~7) << 4) + (((row ^ u) & 7) << 4);
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-
-// dst <- row `lane` of the warp's 32 rows; src_of(lr) is the global address of local row lr (nullptr = zeros).
-template <int D, typename SrcOf>
-__device__ __forceinline__ void warp_load_rows(float (&dst)[D], uint32_t scratch, int row0, int lane, SrcOf src_of) {
-  constexpr int U = D / 4, RPI = 32 / U;
-  static_assert(U <= 32 && 32 % U == 0, "row must be 1..32 16-byte units");
-#pragma unroll
-  for (int g = 0; g < 32 / RPI; ++g) {
-    const int lr = g * RPI + lane / U, u = lane % U;
-    const float* src = src_of(lr);
-    const float4 v = src != nullptr ? __ldg(reinterpret_cast<const float4*>(src) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-    sts128(xpose_addr<D>(scratch, row0 + lr, u), v);
-  }
-  __syncwarp();
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const float4 v = lds128(xpose_addr<D>(scratch, row0 + lane, u));
-    dst[4 * u] = v.x, dst[4 * u + 1] = v.y, dst[4 * u + 2] = v.z, dst[4 * u + 3] = v.w;
-  }
-  __syncwarp();
-}
-
-// row `lane` (src) -> global; dst_of(lr) is the global address of local row lr (nullptr = skip).
-template <int D, typename DstOf>
-__device__ __forceinline__ void warp_store_rows(const float (&src)[D], uint32_t scratch, int row0, int lane, DstOf dst_of) {
-  constexpr int U = D / 4, RPI = 32 / U;
-#pragma unroll
-  for (int u = 0; u < U; ++u)
-    sts128(xpose_addr<D>(scratch, row0 + lane, u), make_float4(src[4 * u], src[4 * u + 1], src[4 * u + 2], src[4 * u + 3]));
-  __syncwarp();
-#pragma unroll
-  for (int g = 0; g < 32 / RPI; ++g) {
-    const int lr = g * RPI + lane / U, u = lane % U;
-    float* dst = dst_of(lr);
-    const float4 v = lds128(xpose_addr<D>(scratch, row0 + lr, u));
-    if (dst != nullptr) reinterpret_cast<float4*>(dst)[u] = v;
-  }
-  __syncwarp();
-}
-
-template <int NWG>
-struct Roles {
-  static constexpr int kEpiWarps = NWG * 4;
-  static constexpr int kProducerWarp = NWG * 4;
-  static constexpr int kMmaWarp = NWG * 4 + 1;
-  // the helper warpgroup (TMA producer, MMA issuer, two idle warps) gives its registers to the epilogue warpgroups
-  static constexpr int kThreads = (NWG * 4 + 4) * 32;
-  // setmaxnreg only MOVES registers inside the CTA's launch allocation (kLaunchRegs per thread, what ptxas assigns
-  // under __launch_bounds__(kThreads, 1)); asking for more leaves some warps spinning in the allocation forever.
-  // launch_wg() checks kLaunchRegs against cudaFuncGetAttributes before every launch.
-  static constexpr int kWarps = NWG * 4 + 4;
-  static constexpr int kLaunchRegs = NWG == 4 ? 96 : 168;
-  static constexpr int kHelperRegs = 56;
-  static constexpr int kEpiRegs = ((kLaunchRegs * kWarps - 4 * kHelperRegs) / (NWG * 4)) / 8 * 8;
-  static_assert(kEpiRegs * NWG * 4 + kHelperRegs * 4 <= kLaunchRegs * kWarps, "register hand-over exceeds the launch allocation");
-  static constexpr int kAccCols = kTmemCols / NWG;  // fp32 accumulator columns of one warpgroup
-};
-
-// issue the 3*D/16 + 1 MMAs of one unit (`ncols` codes starting at code `col0` of the staged N tile).
+// issue the 3*D/16 + 1 MMAs of one unit (128 codes starting at code `col0` of the staged image) and commit them.
 // Called by ONE elected thread.  Descriptors are assembled from 32-bit words so that stepping through K chunks is
-// one add per operand (address field in 16-byte units: A chunk = 128 rows x 16 B = 128 units, B chunk = ntile).
+// one add per operand (address field in 16-byte units: A chunk = 128 rows x 16 B = 128 units, B chunk = 256).
 template <int D>
 __device__ __forceinline__ void issue_unit(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t ones, uint32_t b_tile,
-                                           int ntile, int col0, int ncols, uint32_t bar_full) {
-  const uint32_t idesc = ptx::umma_idesc_bf16(kTileRows, ncols);
+                                           int col0, uint32_t bar_full) {
+  constexpr uint32_t idesc = ptx::umma_idesc_bf16(kTileRows, kUnitCols);
   const uint32_t hi = ptx::umma_desc_hi(128);
-  const uint32_t chunk_b = ntile * 16;                            // bytes between K chunks of the B image
-  const uint32_t a_step = 2 * kTileRows, b_step = 2 * ntile;     // one K=16 step = two chunks, in 16-byte units
+  constexpr uint32_t chunk_b = kNTile * 16;                        // bytes between K chunks of the B image
+  constexpr uint32_t a_step = 2 * kTileRows, b_step = 2 * kNTile;  // one K=16 step = two chunks, in 16-byte units
   const uint32_t d_ahi = ptx::umma_desc_lo(a_hi, kTileRows * 16), d_alo = ptx::umma_desc_lo(a_lo, kTileRows * 16);
   const uint32_t d_one = ptx::umma_desc_lo(ones, kTileRows * 16);
   const uint32_t b_hi = b_tile + col0 * 16;
@@ -320,41 +260,98 @@ __device__ __forceinline__ void issue_unit(uint32_t acc, uint32_t a_hi, uint32_t
   ptx::umma_commit(bar_full);
 }
 
-template <int D, bool ROT, int NWG>
-__global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcParams p) {
-  using R = Roles<NWG>;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  // [A wg0 (hi | lo) | ... | A wg(NWG-1) | ones | barriers (1 KB) | B stages ...]
-  uint8_t* s_a = smem;
-  uint8_t* s_ones = smem + NWG * p.a_bytes;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ones + kOnesBytes);
-  uint8_t* s_b = s_ones + kOnesBytes + 1024;
+// Scan of one accumulator (256 columns, this thread's row, this thread's 64 columns of each unit); see the file
+// header.  Returns the row maximum over the thread's 128 columns and its first column.
+//   acc_addr  TMEM address of (lane quarter, slot accumulator column 0);  h = which 64 columns of each unit
+__device__ __forceinline__ void scan_accumulator(uint32_t acc_addr, int h, uint32_t bar_u0, uint32_t bar_u1, uint32_t phase,
+                                                 bool row_valid, float& m_out, int& col_out) {
+  uint32_t g[32], v[32];
+  const uint32_t c0 = acc_addr + 64 * h;
+  ptx::mbar_wait(bar_u0, phase);
+  ptx::tc_fence_after_sync();
+  ptx::tmem_ld_32x32(c0, g);
+  ptx::tmem_wait_ld(g);
+  const float cm0 = max32(g);
+  ptx::tmem_ld_32x32(c0 + 32, v);
+  ptx::tmem_wait_ld(v);
+  const float cm1 = max32(v);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) g[j] = __float_as_uint(fmaxf(__uint_as_float(g[j]), __uint_as_float(v[j])));
+  ptx::mbar_wait(bar_u1, phase);
+  ptx::tc_fence_after_sync();
+  ptx::tmem_ld_32x32(c0 + kUnitCols, v);
+  ptx::tmem_wait_ld(v);
+  const float cm2 = max32(v);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) g[j] = __float_as_uint(fmaxf(__uint_as_float(g[j]), __uint_as_float(v[j])));
+  ptx::tmem_ld_32x32(c0 + kUnitCols + 32, v);
+  ptx::tmem_wait_ld(v);
+  const float cm3 = max32(v);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) g[j] = __float_as_uint(fmaxf(__uint_as_float(g[j]), __uint_as_float(v[j])));
 
-  uint64_t* bar_b_full = s_bar;                       // [kMaxStages]
-  uint64_t* bar_b_empty = s_bar + kMaxStages;         // [kMaxStages]
-  uint64_t* bar_acc_full = s_bar + 2 * kMaxStages;    // [kMaxWg]  MMA -> epilogue (tcgen05.commit needs an mbarrier)
-  // epilogue -> MMA issuer progress counters, polled by ONE thread: a plain LDS answers in ~30 cycles where an
-  // mbarrier probe takes ~150, and the issuer has up to 2 x NWG conditions to watch
-  uint32_t* cnt_a_ready = reinterpret_cast<uint32_t*>(bar_acc_full + kMaxWg);  // [kMaxWg] warp arrivals: 4 per staged level
-  uint32_t* cnt_acc_empty = cnt_a_ready + kMaxWg;                              // [kMaxWg] warp arrivals: 4 per drained unit
-  uint32_t* s_tmem = cnt_acc_empty + kMaxWg;
+  const float m = fmaxf(max3(cm0, cm1, cm2), cm3);
+  // class of the maximiser on the FMA pipe: acc = sum_j [g_j == m] * (64 + j), four partial sums for ILP
+  float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float e = __saturatef(fmaf(__uint_as_float(g[j]) - m, kBig, 1.0f));
+    acc4[j & 3] = fmaf(e, static_cast<float>(64 + j), acc4[j & 3]);
+  }
+  const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+  const bool e0 = cm0 == m, e1 = cm1 == m, e2 = cm2 == m, e3 = cm3 == m;
+  const int n_chunks = static_cast<int>(e0) + static_cast<int>(e1) + static_cast<int>(e2) + static_cast<int>(e3);
+  const int chunk_col = e0 ? 0 : e1 ? 32 : e2 ? kUnitCols : kUnitCols + 32;
+  // exactly one class and one chunk attain m; a thread whose columns are all padding (m = -1e30) cannot win anyway
+  const bool unique = (acc < 128.f && n_chunks == 1) || m < -1e29f;
+  float best = m;
+  int col = 64 * h + chunk_col + static_cast<int>(acc) - 64;
+  if (__any_sync(0xffffffffu, !unique && row_valid)) {
+    // more than one maximiser somewhere in this warp (duplicate code rows, all-zero input, ...): exact first index
+    best = -INFINITY;
+    col = 0;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int off = 64 * h + (c & 1) * 32 + (c >> 1) * kUnitCols;
+      ptx::tmem_ld_32x32(acc_addr + off, v);
+      ptx::tmem_wait_ld(v);
+      scan_chunk_exact(v, off, best, col);
+    }
+  }
+  m_out = best;
+  col_out = col;
+}
+
+template <int D, bool ROT>
+__global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcParams p) {
+  using L = Rc<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // [A slot0 (hi | lo) | A slot1 | ones | candidates | barriers | B stages ...]
+  uint8_t* s_a = smem;
+  uint8_t* s_ones = smem + kSlots * p.a_bytes;
+  uint8_t* s_cand = s_ones + kOnesBytes;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cand + kCandBytes);
+  uint8_t* s_b = s_cand + kCandBytes + kBarBytes;
+
+  uint64_t* bar_b_full = s_bar;                     // [kMaxStages]  TMA -> MMA issuers
+  uint64_t* bar_b_empty = s_bar + kMaxStages;       // [kMaxStages]  MMA completion (one commit per active slot) -> TMA
+  uint64_t* bar_unit = s_bar + 2 * kMaxStages;      // [kSlots][2]   MMA completion of a unit -> the slot's scan
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_unit + 2 * kSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int tpc = p.tiles_per_cta;
 
-  if (warp == R::kProducerWarp && lane == 0) {
-    for (int s = 0; s < kMaxStages; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bar_b_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bar_b_empty[s]), 1);
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < kMaxStages; ++s) {
+        ptx::mbar_init(ptx::smem_u32(&bar_b_full[s]), 1);
+        ptx::mbar_init(ptx::smem_u32(&bar_b_empty[s]), tpc);
+      }
+      for (int i = 0; i < 2 * kSlots; ++i) ptx::mbar_init(ptx::smem_u32(&bar_unit[i]), 1);
+      ptx::fence_mbar_init();
     }
-    for (int w = 0; w < kMaxWg; ++w) {
-      ptx::mbar_init(ptx::smem_u32(&bar_acc_full[w]), 1);
-      cnt_a_ready[w] = 0;
-      cnt_acc_empty[w] = 0;
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == R::kMmaWarp) {
+    __syncwarp();
     ptx::tmem_alloc(ptx::smem_u32(s_tmem), kTmemCols);
     ptx::tmem_relinquish();
   }
@@ -371,227 +368,250 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
   const uint32_t tmem_base = *s_tmem;
 
   const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
-  const int tpc = p.tiles_per_cta;
   const int64_t n_groups = (n_row_tiles + tpc - 1) / tpc;  // one CTA iteration handles a group of tpc row tiles
   const int total_tiles = a.n_levels * p.n_ktiles;
-  const int units_per_tile = (p.ntile + R::kAccCols - 1) / R::kAccCols;
+  // operand images this CTA consumes in all: the ring (streamed mode) is refilled by slot 0's MMA issuer
+  const uint32_t n_images =
+      static_cast<uint32_t>(((n_groups - 1 - blockIdx.x) / gridDim.x + 1) * total_tiles);
+  auto load_image = [&](uint32_t i) {  // image i of this CTA's sequence -> its stage (one thread)
+    const int s = p.resident ? static_cast<int>(i) : static_cast<int>(i % p.stages);
+    const uint32_t bar = ptx::smem_u32(&bar_b_full[s]);
+    ptx::mbar_arrive_expect_tx(bar, p.tile_bytes);
+    ptx::bulk_g2s(ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes),
+                  p.packed + static_cast<size_t>(i % total_tiles) * p.tile_bytes, p.tile_bytes, bar);
+  };
+  if (threadIdx.x == 0) {
+    // resident: every image once; streamed: fill all stages but one (the issuer adds one image per iteration)
+    const uint32_t first = p.resident ? static_cast<uint32_t>(total_tiles)
+                                      : (n_images < static_cast<uint32_t>(p.stages - 1) ? n_images : p.stages - 1);
+    for (uint32_t i = 0; i < first; ++i) load_image(i);
+  }
 
-  if (warp < R::kEpiWarps) {
-    ptx::setmaxnreg_inc<R::kEpiRegs>();  // registers handed over by the helper warpgroup below
-    if ((warp >> 2) < tpc) {
-    // ===================================== epilogue warpgroups ============================================
-    const int w = warp >> 2;                       // warpgroup = which row tile of the group / which accumulator
-    const int row_in_tile = threadIdx.x - w * kTileRows;
-    const int quarter = warp & 3;                  // TMEM lanes [32*quarter, 32*quarter + 32)
-    uint8_t* a_hi = s_a + w * p.a_bytes;
-    uint8_t* a_lo = a_hi + p.a_bytes / 2;
-    const uint32_t acc_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + w * R::kAccCols;
-    const uint32_t cnt_ready = ptx::smem_u32(&cnt_a_ready[w]);
-    const uint32_t bar_full = ptx::smem_u32(&bar_acc_full[w]);
-    const uint32_t cnt_empty = ptx::smem_u32(&cnt_acc_empty[w]);
-    uint32_t acc_phase = 0;
-    const uint32_t scratch = ptx::smem_u32(a_hi);   // transpose scratch = this warpgroup's A buffer (see above)
-    const int row0 = quarter * 32;                  // first tile row of this warp
+  {
+    const int slot = warp / kSlotWarps;
+    if (slot < tpc) {
+      // ========================================= slot warps ===================================================
+      const int wt = warp % kSlotWarps;
+      const int q = wt & 3;   // TMEM lane quarter of the scan
+      const int h = wt >> 2;  // which 64 columns of each unit this thread scans
+      const int scan_row = q * 32 + lane;
+      const uint32_t acc_col = tmem_base + slot * kNTile;
+      const uint32_t acc_addr = acc_col + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t a_hi = ptx::smem_u32(s_a + slot * p.a_bytes);
+      const uint32_t a_lo = a_hi + p.a_bytes / 2;
+      const uint32_t ones = ptx::smem_u32(s_ones);
+      const uint32_t bar_u0 = ptx::smem_u32(&bar_unit[2 * slot]), bar_u1 = ptx::smem_u32(&bar_unit[2 * slot + 1]);
+      uint2* cand = reinterpret_cast<uint2*>(s_cand) + slot * 2 * kTileRows;  // [half][row] = (max bits, column)
+      const uint32_t bar_scan = 1 + slot, bar_issue = 1 + kSlots + slot;      // named barriers of this slot
+      // row-cooperative coordinates
+      const int j = lane % L::RPI, kc = lane / L::RPI;
+      const int rc_row0 = 16 * wt + j;  // + g * RPI
+      const bool want_loss = a.loss != nullptr || a.level_loss != nullptr;
+      uint32_t unit_phase = 0;
+      uint32_t it = 0;  // operand images consumed so far (ring position in streamed mode)
 
-    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-      const int64_t warp_row0 = (tpc * grp + w) * kTileRows + row0;  // global row of the warp's local row 0
-      const int64_t row = warp_row0 + lane;
-      const bool valid = row < a.n;
-      float r[D];
-      warp_load_rows<D>(r, scratch, row0, lane,
-                        [&](int lr) { return warp_row0 + lr < a.n ? a.x + (warp_row0 + lr) * D : nullptr; });
-      float total_loss = 0.f;
-      for (int l = 0; l < a.n_levels; ++l) {
-        if (a.residuals != nullptr) {
-          float* base = a.residuals + static_cast<int64_t>(l) * a.n * D;
-          warp_store_rows<D>(r, scratch, row0, lane,
-                             [&](int lr) { return warp_row0 + lr < a.n ? base + (warp_row0 + lr) * D : nullptr; });
-        }
-        stage_a_operand<D>(a_hi, a_lo, row_in_tile, r);
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) ptx::counter_add_release(cnt_ready, 1);
-
-        float best = -INFINITY;
-        int best_k = 0;
-        for (int t = 0; t < p.n_ktiles; ++t) {
-          for (int u = 0; u < units_per_tile; ++u) {
-            const int col0 = u * R::kAccCols;
-            const int n_chunks = min(R::kAccCols, p.ntile - col0) / 32;
-            ptx::mbar_wait(bar_full, acc_phase);
-            acc_phase ^= 1;
-            ptx::tc_fence_after_sync();
-            for (int c = 0; c < n_chunks; ++c) {
-              uint32_t v[32];
-              ptx::tmem_ld_32x32(acc_addr + c * 32, v);
-              ptx::tmem_wait_ld(v);
-              scan_chunk(v, t * p.ntile + col0 + c * 32, best, best_k);
-            }
-            ptx::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) ptx::counter_add_release(cnt_empty, 1);
-          }
-        }
-        best_k = min(best_k, a.k - 1);
-
-        // every MMA of this level has completed (last acc_full observed): the A buffer is free to be the scratch
-        const float* cb = a.codebooks + static_cast<int64_t>(l) * a.k * D;
-        float e[D], o[D];
-        warp_load_rows<D>(e, scratch, row0, lane, [&](int lr) {
-          return cb + static_cast<int64_t>(__shfl_sync(0xffffffffu, best_k, lr)) * D;
-        });
-        const float ll = rq_level_tail_o<D, ROT>(r, e, a.beta, o);
-        if (a.emb_out != nullptr) {
-          float* base = a.emb_out + static_cast<int64_t>(l) * a.n * D;
-          warp_store_rows<D>(o, scratch, row0, lane,
-                             [&](int lr) { return warp_row0 + lr < a.n ? base + (warp_row0 + lr) * D : nullptr; });
-        }
-        total_loss += ll;
-        if (valid) {
-          a.ids[row * a.ids_row_stride + l * a.ids_level_stride] = best_k;
-          if (a.level_loss != nullptr) a.level_loss[static_cast<int64_t>(l) * a.n + row] = ll;
-        }
-      }
-      if (valid && a.loss != nullptr) a.loss[row] = total_loss;
-      if (a.final_residual != nullptr)
-        warp_store_rows<D>(r, scratch, row0, lane,
-                           [&](int lr) { return warp_row0 + lr < a.n ? a.final_residual + (warp_row0 + lr) * D : nullptr; });
-    }
-    }  // else: warpgroup without a row tile (small N: fewer tiles per CTA so that more SMs work)
-  } else {
-    ptx::setmaxnreg_dec<R::kHelperRegs>();
-    if (warp == R::kProducerWarp) {
-    // ===================================== TMA producer ===================================================
-    if (lane == 0) {
-      if (p.resident) {
-        if (static_cast<int64_t>(blockIdx.x) < n_groups) {
-          for (int s = 0; s < total_tiles; ++s) {
-            const uint32_t bar = ptx::smem_u32(&bar_b_full[s]);
-            ptx::mbar_arrive_expect_tx(bar, p.tile_bytes);
-            ptx::bulk_g2s(ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes),
-                          p.packed + static_cast<size_t>(s) * p.tile_bytes, p.tile_bytes, bar);
-          }
-        }
-      } else {
-        uint32_t it = 0;
-        for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-          for (int tile = 0; tile < total_tiles; ++tile, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
-            ptx::mbar_wait(ptx::smem_u32(&bar_b_empty[s]), ph ^ 1);
-            const uint32_t bar = ptx::smem_u32(&bar_b_full[s]);
-            ptx::mbar_arrive_expect_tx(bar, p.tile_bytes);
-            ptx::bulk_g2s(ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes),
-                          p.packed + static_cast<size_t>(tile) * p.tile_bytes, p.tile_bytes, bar);
-          }
-        }
-      }
-    }
-    } else if (warp == R::kMmaWarp) {
-    // ===================================== MMA issuer =====================================================
-    const uint32_t ones = ptx::smem_u32(s_ones);
-    if (p.resident) {
-      // Every operand image is resident: the warpgroups are independent, so serve whichever one is ready
-      // (its residual staged and its accumulator drained) instead of a fixed round that blocks on the slowest.
-      if (static_cast<int64_t>(blockIdx.x) < n_groups)
-        for (int s = 0; s < total_tiles; ++s) ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), 0);
-      const int64_t my_groups = static_cast<int64_t>(blockIdx.x) < n_groups
-                                    ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-      const int units_per_level = p.n_ktiles * units_per_tile;
-      const uint32_t units_per_wg = static_cast<uint32_t>(my_groups * a.n_levels * units_per_level);
-      {
-        // The whole warp runs the scheduler with warp-uniform state (lane 0's view of the counters decides); the
-        // MMAs and the commit are issued by one elected lane.
-        uint32_t done[NWG];         // units issued so far
-        uint32_t in_level[NWG];     // position of the next unit inside its level
-        uint32_t level[NWG];        // level of the next unit
-        uint32_t levels_seen[NWG];  // number of staged residuals already consumed
-#pragma unroll
-        for (int w = 0; w < NWG; ++w) done[w] = in_level[w] = level[w] = levels_seen[w] = 0;
-        int remaining = tpc;
-        long long idle_since = 0;
-        while (remaining > 0) {
-          bool progressed = false;
-#pragma unroll
-          for (int w = 0; w < NWG; ++w) {
-            if (w >= tpc || done[w] >= units_per_wg) continue;
-            // residual of this unit's level staged by all 4 warps?  accumulator drained of every earlier unit?
-            const uint32_t ready = __shfl_sync(0xffffffffu, ptx::counter_ld_acquire(ptx::smem_u32(&cnt_a_ready[w])), 0);
-            if (static_cast<int32_t>(ready - 4 * (levels_seen[w] + 1)) < 0) continue;
-            const uint32_t drained = __shfl_sync(0xffffffffu, ptx::counter_ld_acquire(ptx::smem_u32(&cnt_acc_empty[w])), 0);
-            if (static_cast<int32_t>(drained - 4 * done[w]) < 0) continue;
-            ptx::tc_fence_after_sync();
-            if (ptx::elect_one()) {
-              const int t = in_level[w] / units_per_tile, u = in_level[w] % units_per_tile;
-              const int col0 = u * R::kAccCols;
-              const int ncols = min(R::kAccCols, p.ntile - col0);
-              const uint32_t a_hi = ptx::smem_u32(s_a + w * p.a_bytes);
-              issue_unit<D>(tmem_base + w * R::kAccCols, a_hi, a_hi + p.a_bytes / 2, ones,
-                            ptx::smem_u32(s_b + static_cast<size_t>(level[w] * p.n_ktiles + t) * p.tile_bytes), p.ntile, col0,
-                            ncols, ptx::smem_u32(&bar_acc_full[w]));
-            }
-            __syncwarp();
-            done[w]++;
-            if (++in_level[w] == static_cast<uint32_t>(units_per_level)) {  // next unit opens a new level
-              in_level[w] = 0;
-              level[w] = level[w] + 1 == static_cast<uint32_t>(a.n_levels) ? 0 : level[w] + 1;
-              levels_seen[w]++;
-            }
-            if (done[w] >= units_per_wg) remaining--;
-            progressed = true;
-          }
-          if (progressed) {
-            idle_since = 0;
-          } else {
-            if (idle_since == 0) idle_since = clock64();
-            if (clock64() - idle_since > 4000000000LL) {
-              if (lane == 0) printf("hidvae_b200: MMA scheduler starved (block %d)\n", blockIdx.x);
-              __trap();
-            }
-          }
-        }
-      }
-      __syncwarp();
-    } else {
-      // Streamed operand images: all warpgroups consume the same stage in lock step (one load serves tpc tiles).
-      uint32_t it = 0;
-      uint32_t levels_seen[kMaxWg] = {0, 0, 0, 0};
-      uint32_t acc_uses[kMaxWg] = {0, 0, 0, 0};
       for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        for (int tile = 0; tile < total_tiles; ++tile, ++it) {
-          const int t = tile % p.n_ktiles;
-          const int s = it % p.stages;
-          ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), (it / p.stages) & 1);
-          const uint32_t b_tile = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
-          for (int w = 0; w < tpc; ++w) {
-            if (t == 0) {
-              levels_seen[w]++;
-              ptx::counter_wait(ptx::smem_u32(&cnt_a_ready[w]), 4 * levels_seen[w]);
+        const int64_t tile_row0 = (tpc * grp + slot) * kTileRows;  // may lie beyond n: the slot then runs on zeros
+        if (threadIdx.x % kSlotThreads == 0) {  // pull the slot's next row tile into L2 while this one is processed
+          const int64_t next_row0 = tile_row0 + static_cast<int64_t>(gridDim.x) * tpc * kTileRows;
+          if (next_row0 < a.n) {
+            const int64_t rows = a.n - next_row0 < kTileRows ? a.n - next_row0 : kTileRows;
+            ptx::bulk_prefetch_l2(a.x + next_row0 * D, static_cast<uint32_t>(rows * D * 4));
+          }
+        }
+        float r[L::RPT][8];
+        float total_loss[L::RPT];
+#pragma unroll
+        for (int g = 0; g < L::RPT; ++g) {
+          const int64_t grow = tile_row0 + rc_row0 + g * L::RPI;
+          total_loss[g] = 0.f;
+          if (grow < a.n) {
+            const float4* src = reinterpret_cast<const float4*>(a.x + grow * D + kc * 8);
+            const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+            r[g][0] = v0.x, r[g][1] = v0.y, r[g][2] = v0.z, r[g][3] = v0.w;
+            r[g][4] = v1.x, r[g][5] = v1.y, r[g][6] = v1.z, r[g][7] = v1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[g][i] = 0.f;
+          }
+        }
+
+        for (int l = 0; l < a.n_levels; ++l) {
+          // ---- stage the residual as the A operand (bf16 hi | lo), optionally store it ----
+#pragma unroll
+          for (int g = 0; g < L::RPT; ++g) {
+            const int row = rc_row0 + g * L::RPI;
+            uint4 hi, lo;
+            split8(r[g], hi, lo);
+            sts128(a_hi + kc * (kTileRows * 16) + row * 16, hi);
+            sts128(a_lo + kc * (kTileRows * 16) + row * 16, lo);
+            if (a.residuals != nullptr) {
+              const int64_t grow = tile_row0 + row;
+              if (grow < a.n) {
+                float4* dst = reinterpret_cast<float4*>(a.residuals + (static_cast<int64_t>(l) * a.n + grow) * D + kc * 8);
+                dst[0] = make_float4(r[g][0], r[g][1], r[g][2], r[g][3]);
+                dst[1] = make_float4(r[g][4], r[g][5], r[g][6], r[g][7]);
+              }
             }
-            for (int u = 0; u < units_per_tile; ++u) {
-              ptx::counter_wait(ptx::smem_u32(&cnt_acc_empty[w]), 4 * acc_uses[w]);
-              acc_uses[w]++;
+          }
+          ptx::fence_proxy_async_smem();
+
+          float best = -INFINITY;
+          int best_col = 0;
+          for (int t = 0; t < p.n_ktiles; ++t, ++it) {
+            // ---- slot barrier: A staged (t == 0) / accumulator drained (t > 0); warp 0 of the slot issues ----
+            ptx::tc_fence_before_sync();
+            if (wt == 0) {
+              ptx::named_bar_sync(bar_issue, kSlotThreads);
+              const int s = p.resident ? l * p.n_ktiles + t : static_cast<int>(it % p.stages);
+              const uint32_t b_phase = p.resident ? 0u : (it / p.stages) & 1u;
+              ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), b_phase);
               ptx::tc_fence_after_sync();
               if (ptx::elect_one()) {
-                const int col0 = u * R::kAccCols;
-                const uint32_t a_hi = ptx::smem_u32(s_a + w * p.a_bytes);
-                issue_unit<D>(tmem_base + w * R::kAccCols, a_hi, a_hi + p.a_bytes / 2, ones, b_tile, p.ntile, col0,
-                              min(R::kAccCols, p.ntile - col0), ptx::smem_u32(&bar_acc_full[w]));
+                const uint32_t b_tile = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
+                issue_unit<D>(acc_col, a_hi, a_lo, ones, b_tile, 0, bar_u0);
+                issue_unit<D>(acc_col + kUnitCols, a_hi, a_lo, ones, b_tile, kUnitCols, bar_u1);
+                if (!p.resident) {
+                  ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
+                  if (slot == 0) {
+                    // refill: image it + stages - 1 goes where image it - 1 was, once every slot's MMAs on it are done
+                    const uint32_t nxt = it + p.stages - 1;
+                    if (nxt < n_images) {
+                      if (it > 0) {
+                        const uint32_t prev = it - 1;
+                        ptx::mbar_wait(ptx::smem_u32(&bar_b_empty[prev % p.stages]), (prev / p.stages) & 1u);
+                      }
+                      load_image(nxt);
+                    }
+                  }
+                }
               }
               __syncwarp();
+            } else {
+              ptx::named_bar_arrive(bar_issue, kSlotThreads);
+            }
+            // ---- scan ----
+            float m;
+            int col;
+            scan_accumulator(acc_addr, h, bar_u0, bar_u1, unit_phase, tile_row0 + scan_row < a.n, m, col);
+            unit_phase ^= 1;
+            if (m > best) {  // strict: an earlier image keeps exact ties
+              best = m;
+              best_col = t * kNTile + col;
             }
           }
-          if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
-          __syncwarp();
+          cand[h * kTileRows + scan_row] = make_uint2(__float_as_uint(best), static_cast<uint32_t>(best_col));
+          ptx::tc_fence_before_sync();
+          ptx::named_bar_sync(bar_scan, kSlotThreads);
+
+          // ---- row work: combine the two halves, gather the code row, value / loss / next residual ----
+          const float* cb = a.codebooks + static_cast<int64_t>(l) * a.k * D;
+          float e[L::RPT][8];
+          int idx[L::RPT];
+#pragma unroll
+          for (int g = 0; g < L::RPT; ++g) {
+            const int row = rc_row0 + g * L::RPI;
+            const uint2 c0 = cand[row], c1 = cand[kTileRows + row];
+            const float m0 = __uint_as_float(c0.x), m1 = __uint_as_float(c1.x);
+            const bool first = m0 > m1 || (m0 == m1 && c0.y < c1.y);  // lowest column wins exact ties
+            int k_sel = static_cast<int>(first ? c0.y : c1.y);
+            k_sel = k_sel < a.k ? k_sel : a.k - 1;
+            idx[g] = k_sel;
+            const float4* src = reinterpret_cast<const float4*>(cb + static_cast<int64_t>(k_sel) * D + kc * 8);
+            const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+            e[g][0] = v0.x, e[g][1] = v0.y, e[g][2] = v0.z, e[g][3] = v0.w;
+            e[g][4] = v1.x, e[g][5] = v1.y, e[g][6] = v1.z, e[g][7] = v1.w;
+          }
+#pragma unroll
+          for (int g = 0; g < L::RPT; ++g) {
+            const int64_t grow = tile_row0 + rc_row0 + g * L::RPI;
+            const bool valid = grow < a.n;
+            float o[8];
+            float ll = 0.f;
+            if (want_loss) {
+              float s = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float df = r[g][i] - e[g][i];
+                s = fmaf(df, df, s);
+              }
+              s = row_sum<D>(s);
+              ll = s + a.beta * s;  // (modules/loss.py:41-44)
+            }
+            if constexpr (!ROT) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = e[g][i];
+            } else {
+              // modules/quantize.py:34-45,134-140:  o = r - 2 (r.w) w + 2 (r.u) q
+              float rr = 0.f, ee = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                rr = fmaf(r[g][i], r[g][i], rr);
+                ee = fmaf(e[g][i], e[g][i], ee);
+              }
+              rr = row_sum<D>(rr);
+              ee = row_sum<D>(ee);
+              const float inv_r = 1.0f / (sqrtf(rr) + 1e-8f);  // u = r / (|r| + 1e-8)
+              const float inv_e = 1.0f / (sqrtf(ee) + 1e-8f);  // q = e / (|e| + 1e-8)
+              float ss = 0.f, ru = 0.f, rs = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float u = r[g][i] * inv_r;
+                const float qv = e[g][i] * inv_e;
+                const float s = u + qv;
+                ss = fmaf(s, s, ss);
+                ru = fmaf(r[g][i], u, ru);
+                rs = fmaf(r[g][i], s, rs);
+              }
+              ss = row_sum<D>(ss);
+              ru = row_sum<D>(ru);
+              rs = row_sum<D>(rs);
+              const float inv_s = 1.0f / fmaxf(sqrtf(ss), 1e-6f);  // w = (u+q) / max(|u+q|, 1e-6)
+              const float rw2 = 2.0f * (rs * inv_s);               // 2 (r.w)
+              const float ru2 = 2.0f * ru;                         // 2 (r.u)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float u = r[g][i] * inv_r;
+                const float qv = e[g][i] * inv_e;
+                const float w = (u + qv) * inv_s;
+                o[i] = r[g][i] - rw2 * w + ru2 * qv;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[g][i] = r[g][i] - o[i];
+            total_loss[g] += ll;
+            if (valid) {
+              if (a.emb_out != nullptr) {
+                float4* dst = reinterpret_cast<float4*>(a.emb_out + (static_cast<int64_t>(l) * a.n + grow) * D + kc * 8);
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+              }
+              if (kc == 0) {
+                a.ids[grow * a.ids_row_stride + l * a.ids_level_stride] = idx[g];
+                if (a.level_loss != nullptr) a.level_loss[static_cast<int64_t>(l) * a.n + grow] = ll;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < L::RPT; ++g) {
+          const int64_t grow = tile_row0 + rc_row0 + g * L::RPI;
+          if (grow < a.n) {
+            if (kc == 0 && a.loss != nullptr) a.loss[grow] = total_loss[g];
+            if (a.final_residual != nullptr) {
+              float4* dst = reinterpret_cast<float4*>(a.final_residual + grow * D + kc * 8);
+              dst[0] = make_float4(r[g][0], r[g][1], r[g][2], r[g][3]);
+              dst[1] = make_float4(r[g][4], r[g][5], r[g][6], r[g][7]);
+            }
+          }
         }
       }
-    }
-    }
+    }  // else: slot without row tiles (small N: one tile per CTA so that more SMs work)
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == R::kMmaWarp) {
+  if (warp == 0) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -599,36 +619,11 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
 
 template <int D>
 int pack_d(const float* codebooks, int n_levels, int k, const TcPlan& plan, uint8_t* packed, cudaStream_t stream) {
-  const int total_codes = n_levels * plan.n_ktiles * plan.ntile;
-  rq_pack_codebooks_kernel<D><<<(total_codes + 127) / 128, 128, 0, stream>>>(codebooks, n_levels, k, plan.ntile,
-                                                                           plan.n_ktiles, plan.tile_bytes, packed);
+  const int total_codes = n_levels * plan.n_ktiles * kNTile;
+  rq_pack_codebooks_kernel<D><<<(total_codes + 127) / 128, 128, 0, stream>>>(codebooks, n_levels, k, plan.n_ktiles,
+                                                                           plan.tile_bytes, packed);
   HV_CUDA_CHECK(cudaGetLastError());
   return HV_OK;
-}
-
-template <int D, int NWG>
-int launch_wg(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, const DeviceProps& props, cudaStream_t stream) {
-  const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
-  // as many row tiles per CTA as it takes to cover them with one CTA per SM, at most NWG
-  int64_t tpc = (n_row_tiles + props.sm_count - 1) / props.sm_count;
-  tpc = tpc < 1 ? 1 : (tpc > NWG ? NWG : tpc);
-  const int64_t n_groups = (n_row_tiles + tpc - 1) / tpc;
-  const unsigned grid = static_cast<unsigned>(n_groups < props.sm_count ? n_groups : props.sm_count);
-  TcParams p{packed, plan.ntile, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes, static_cast<int>(tpc)};
-  auto go = [&](auto kernel) -> int {
-    cudaFuncAttributes attr;
-    HV_CUDA_CHECK(cudaFuncGetAttributes(&attr, kernel));
-    if (attr.numRegs < Roles<NWG>::kLaunchRegs) {  // would deadlock in setmaxnreg.inc: refuse loudly instead
-      set_error("hv_rq_forward: tcgen05 kernel was built with %d registers/thread, the register hand-over needs %d",
-                attr.numRegs, Roles<NWG>::kLaunchRegs);
-      return HV_ERR_UNSUPPORTED;
-    }
-    HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-    kernel<<<grid, Roles<NWG>::kThreads, plan.smem_bytes, stream>>>(a, p);
-    HV_CUDA_CHECK(cudaGetLastError());
-    return HV_OK;
-  };
-  return rot ? go(rq_fwd_tc_kernel<D, true, NWG>) : go(rq_fwd_tc_kernel<D, false, NWG>);
 }
 
 template <int D>
@@ -637,26 +632,46 @@ int launch_d(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, 
     if (int st = pack_d<D>(a.codebooks, a.n_levels, a.k, plan, packed, stream)) return st;
   DeviceProps props;
   if (int st = device_props(&props)) return st;
-  return plan.n_wg == 4 ? launch_wg<D, 4>(a, rot, plan, packed, props, stream) : launch_wg<D, 2>(a, rot, plan, packed, props, stream);
+  const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
+  // two row tiles per CTA as soon as one per SM does not cover them
+  const int tpc = n_row_tiles > props.sm_count ? kSlots : 1;
+  const int64_t n_groups = (n_row_tiles + tpc - 1) / tpc;
+  const unsigned grid = static_cast<unsigned>(n_groups < props.sm_count ? n_groups : props.sm_count);
+  TcParams p{packed, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes, tpc};
+  auto go = [&](auto kernel) -> int {
+    HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    kernel<<<grid, kThreads, plan.smem_bytes, stream>>>(a, p);
+    HV_CUDA_CHECK(cudaGetLastError());
+    return HV_OK;
+  };
+  return rot ? go(rq_fwd_tc_kernel<D, true>) : go(rq_fwd_tc_kernel<D, false>);
+}
+
+bool use_v4() {
+  static const bool v4 = [] {
+    const char* e = getenv("HIDVAE_TC_IMPL");
+    return e != nullptr && e[0] == 'v' && e[1] == '4';
+  }();
+  return v4;
 }
 
 }  // namespace
 
 bool rq_fwd_tc_supported(int d, int k, int n_levels) {
   TcPlan plan;
-  return (d == 16 || d == 32 || d == 64) && make_plan(d, k, n_levels, &plan);
+  return make_plan(d, k, n_levels, &plan);
 }
 
 size_t rq_fwd_tc_workspace_bytes(int d, int k, int n_levels) {
   TcPlan plan;
-  if (!rq_fwd_tc_supported(d, k, n_levels) || !make_plan(d, k, n_levels, &plan)) return 0;
+  if (!make_plan(d, k, n_levels, &plan)) return 0;
   return static_cast<size_t>(n_levels) * plan.n_ktiles * plan.tile_bytes;
 }
 
 int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* workspace, size_t workspace_bytes,
                    cudaStream_t stream) {
   TcPlan plan;
-  if (!rq_fwd_tc_supported(d, k, n_levels) || !make_plan(d, k, n_levels, &plan)) {
+  if (!make_plan(d, k, n_levels, &plan)) {
     set_error("hv_rq_pack_codebooks: no tcgen05 instantiation for D=%d K=%d L=%d", d, k, n_levels);
     return HV_ERR_UNSUPPORTED;
   }
@@ -681,7 +696,7 @@ int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* wor
 int launch_rq_fwd_tc(const RqFwdArgs& a, int d, bool rot, void* workspace, size_t workspace_bytes, bool prepacked,
                      cudaStream_t stream) {
   TcPlan plan;
-  if (!rq_fwd_tc_supported(d, a.k, a.n_levels) || !make_plan(d, a.k, a.n_levels, &plan)) {
+  if (!make_plan(d, a.k, a.n_levels, &plan)) {
     set_error("hv_rq_forward: no tcgen05 instantiation for D=%d K=%d L=%d", d, a.k, a.n_levels);
     return HV_ERR_UNSUPPORTED;
   }
@@ -696,6 +711,11 @@ int launch_rq_fwd_tc(const RqFwdArgs& a, int d, bool rot, void* workspace, size_
   }
   if (a.n == 0) return HV_OK;
   uint8_t* packed = static_cast<uint8_t*>(workspace);
+  if (use_v4()) {
+    if (!prepacked)
+      if (int st = launch_rq_pack(a.codebooks, a.n_levels, a.k, d, workspace, workspace_bytes, stream)) return st;
+    return launch_rq_fwd_tc_v4(a, d, rot, workspace, stream);
+  }
   switch (d) {
     case 16: return launch_d<16>(a, rot, plan, packed, prepacked, stream);
     case 32: return launch_d<32>(a, rot, plan, packed, prepacked, stream);

@@ -25,7 +25,7 @@ torch.cuda.set_device(0)
 x, cbs, g_emb, g_loss = bench.synth(args.rows, d, k, L, 7, "cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 packed = ops.pack_codebooks(cbs)
-res = dict(tag=args.tag, nwg=os.environ.get("HIDVAE_TC_NWG", "auto"), rows=args.rows, d=d, k=k, L=L)
+res = dict(tag=args.tag, impl=os.environ.get("HIDVAE_TC_IMPL", "v5"), rows=args.rows, d=d, k=k, L=L)
 t = bench.time_region(lambda: ops.rq_encode(x, cbs, packed=packed), args.reps, 3, flush) / args.reps
 res.update(encode_ms=t, encode_gitems=args.rows / t / 1e6, encode_tflops=2.0 * k * d * L * args.rows / t / 1e9)
 if d <= 32:
