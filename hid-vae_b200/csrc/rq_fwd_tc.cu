@@ -45,16 +45,25 @@ namespace {
 constexpr int kTileRows = 128;
 constexpr int kNTile = 256;                 // codes per operand image (= accumulator columns of a slot)
 constexpr int kUnitCols = 128;              // N of one tcgen05.mma
-constexpr int kSlots = 2;                   // row tiles in flight per CTA
-constexpr int kSlotWarps = 8;
-constexpr int kSlotThreads = kSlotWarps * 32;
-constexpr int kThreads = kSlots * kSlotThreads;  // 512: the register file gives every thread 128 registers
+constexpr int kMaxSlots = 4;                // row tiles in flight per CTA (Cfg<D>::NT of them)
+constexpr int kGroupWarps = 8;              // warps of the row group == warps of the scan group
+constexpr int kThreads = 2 * kGroupWarps * 32;
+constexpr int kRowRegs = 160, kScanRegs = 96;  // setmaxnreg split of the 128-per-thread launch allocation
+static_assert(kRowRegs + kScanRegs == 256, "register hand-over must stay inside the launch allocation");
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 16;
 constexpr int kOnesBytes = 2 * kTileRows * 16;              // one K=16 step of the A operand: [2 chunks][128 rows][8 bf16]
-constexpr int kCandBytes = kSlots * 2 * kTileRows * 8;      // (max, column) per slot, half, row
+constexpr int kCandSlotBytes = 2 * kTileRows * 8;           // (max, column) per half, row of one slot
+constexpr int kLossSlotBytes = kTileRows * 4;               // running loss per row of one slot
 constexpr int kBarBytes = 1024;
 constexpr int kSmemLimit = 227 * 1024;
+
+// row tiles in flight: four while their A operands fit beside the operand images, else two
+template <int D>
+struct Cfg {
+  static constexpr int NT = D <= 32 ? 4 : 2;
+};
+inline int slots_for(int d) { return d <= 32 ? 4 : 2; }
 
 struct TcPlan {
   int n_ktiles;    // operand images per level
@@ -70,7 +79,7 @@ bool make_plan(int d, int k, int n_levels, TcPlan* p) {
   p->n_ktiles = (k + kNTile - 1) / kNTile;
   p->tile_bytes = kNTile * (4 * d + 32);
   p->a_bytes = kTileRows * d * 4;
-  const int fixed = kSlots * p->a_bytes + kOnesBytes + kCandBytes + kBarBytes;
+  const int fixed = slots_for(d) * (p->a_bytes + kCandSlotBytes + kLossSlotBytes) + kOnesBytes + kBarBytes;
   const int budget = kSmemLimit - fixed;
   const long long total_tiles = static_cast<long long>(n_levels) * p->n_ktiles;
   if (total_tiles <= kMaxStages && total_tiles * p->tile_bytes <= budget) {
@@ -151,7 +160,6 @@ struct TcParams {
   int stages;
   int resident;
   int a_bytes;
-  int tiles_per_cta;  // active slots (1 or 2): one when there are not enough row tiles to give every SM two
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -322,35 +330,61 @@ __device__ __forceinline__ void scan_accumulator(uint32_t acc_addr, int h, uint3
   col_out = col;
 }
 
-template <int D, bool ROT>
+// ---------------------------------------------------------------------------------------------------------
+// The kernel: a pipeline between two warp groups of the persistent CTA, all hand-overs are mbarriers.
+//
+//   row group  (warps 0-7)   split in NSLOT sub-groups of 8 / NSLOT warps; a sub-group owns one row tile ("slot") at a
+//                            time in the row-cooperative layout and runs, per level:
+//                              stage the residual as the slot's A operand (bf16 hi | lo)  ->  its first warp issues the
+//                              level's tcgen05.mma into the next free accumulator (2 x 256 TMEM columns used
+//                              alternately; a turn counter keeps the sub-groups in round-robin order)  ->  wait for the
+//                              slot's scan  ->  merge the two half-row candidates, write the id, gather the chosen code
+//                              row  ->  value / loss / next residual.
+//                            The sub-groups are independent instruction streams, so one slot's global-load and MMA
+//                            latencies are covered by the others.
+//   scan group (warps 8-15)  takes the accumulators in issue order: 2-D fold argmax (scan_accumulator), candidate
+//                            (max, column) per half row into shared memory, scan_done[slot] / acc_free[acc].
+// ---------------------------------------------------------------------------------------------------------
+template <int D, bool ROT, int NSLOT>
 __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcParams p) {
   using L = Rc<D>;
+  constexpr int WPS = kGroupWarps / NSLOT;                 // warps per slot
+  constexpr int TPS = WPS * 32;                            // threads per slot
+  constexpr int RPT = kTileRows * L::KC / TPS;             // rows per thread
+  constexpr int GC = RPT < 4 ? RPT : 4;                    // rows gathered at a time
   extern __shared__ __align__(1024) uint8_t smem[];
-  // [A slot0 (hi | lo) | A slot1 | ones | candidates | barriers | B stages ...]
+  // [A slot 0 (hi | lo) | ... | ones | candidates | loss | barriers | B stages ...]   (sized for kMaxSlots slots)
+  constexpr int n_slots_smem = Cfg<D>::NT;
   uint8_t* s_a = smem;
-  uint8_t* s_ones = smem + kSlots * p.a_bytes;
+  uint8_t* s_ones = smem + n_slots_smem * p.a_bytes;
   uint8_t* s_cand = s_ones + kOnesBytes;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cand + kCandBytes);
-  uint8_t* s_b = s_cand + kCandBytes + kBarBytes;
+  float* s_loss = reinterpret_cast<float*>(s_cand + n_slots_smem * kCandSlotBytes);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cand + n_slots_smem * (kCandSlotBytes + kLossSlotBytes));
+  uint8_t* s_b = reinterpret_cast<uint8_t*>(s_bar) + kBarBytes;
 
-  uint64_t* bar_b_full = s_bar;                     // [kMaxStages]  TMA -> MMA issuers
-  uint64_t* bar_b_empty = s_bar + kMaxStages;       // [kMaxStages]  MMA completion (one commit per active slot) -> TMA
-  uint64_t* bar_unit = s_bar + 2 * kMaxStages;      // [kSlots][2]   MMA completion of a unit -> the slot's scan
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_unit + 2 * kSlots);
+  uint64_t* bar_b_full = s_bar;                      // [kMaxStages]  TMA -> MMA issuers
+  uint64_t* bar_b_empty = bar_b_full + kMaxStages;   // [kMaxStages]  MMA completion (one commit per slot) -> TMA
+  uint64_t* bar_mma_done = bar_b_empty + kMaxStages; // [2 acc][2 units]  MMA completion -> scan group
+  uint64_t* bar_acc_free = bar_mma_done + 4;         // [2 acc]       scan group (8 warps) -> MMA issuers
+  uint64_t* bar_scan_done = bar_acc_free + 2;        // [kMaxSlots]   scan group (8 warps) -> the slot's sub-group
+  uint32_t* s_turn = reinterpret_cast<uint32_t*>(bar_scan_done + kMaxSlots);  // number of accumulators issued so far
+  uint32_t* s_tmem = s_turn + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tpc = p.tiles_per_cta;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int s = 0; s < kMaxStages; ++s) {
-        ptx::mbar_init(ptx::smem_u32(&bar_b_full[s]), 1);
-        ptx::mbar_init(ptx::smem_u32(&bar_b_empty[s]), tpc);
-      }
-      for (int i = 0; i < 2 * kSlots; ++i) ptx::mbar_init(ptx::smem_u32(&bar_unit[i]), 1);
-      ptx::fence_mbar_init();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bar_b_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bar_b_empty[s]), NSLOT);
     }
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(ptx::smem_u32(&bar_mma_done[i]), 1);
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(ptx::smem_u32(&bar_acc_free[i]), kGroupWarps);
+    for (int i = 0; i < kMaxSlots; ++i) ptx::mbar_init(ptx::smem_u32(&bar_scan_done[i]), kGroupWarps);
+    *s_turn = 0;
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
     __syncwarp();
     ptx::tmem_alloc(ptx::smem_u32(s_tmem), kTmemCols);
     ptx::tmem_relinquish();
@@ -367,246 +401,282 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
 
+  const int n_levels = a.n_levels, n_k = p.n_ktiles;
   const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
-  const int64_t n_groups = (n_row_tiles + tpc - 1) / tpc;  // one CTA iteration handles a group of tpc row tiles
-  const int total_tiles = a.n_levels * p.n_ktiles;
-  // operand images this CTA consumes in all: the ring (streamed mode) is refilled by slot 0's MMA issuer
-  const uint32_t n_images =
-      static_cast<uint32_t>(((n_groups - 1 - blockIdx.x) / gridDim.x + 1) * total_tiles);
-  auto load_image = [&](uint32_t i) {  // image i of this CTA's sequence -> its stage (one thread)
-    const int s = p.resident ? static_cast<int>(i) : static_cast<int>(i % p.stages);
-    const uint32_t bar = ptx::smem_u32(&bar_b_full[s]);
-    ptx::mbar_arrive_expect_tx(bar, p.tile_bytes);
-    ptx::bulk_g2s(ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes),
-                  p.packed + static_cast<size_t>(i % total_tiles) * p.tile_bytes, p.tile_bytes, bar);
+  const int64_t n_groups = (n_row_tiles + NSLOT - 1) / NSLOT;  // a group = NSLOT consecutive row tiles, one per slot
+  const int my_groups = static_cast<int>((n_groups - 1 - blockIdx.x) / gridDim.x + 1);  // grid <= n_groups
+  const int total_tiles = n_levels * n_k;
+  // first row of slot `slot` in this CTA's k-th group (may lie beyond n: the slot then runs on zeros)
+  auto tile_row0 = [&](int k, int slot) -> int64_t {
+    return ((static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(k) * gridDim.x) * NSLOT + slot) * kTileRows;
   };
-  if (threadIdx.x == 0) {
-    // resident: every image once; streamed: fill all stages but one (the issuer adds one image per iteration)
-    const uint32_t first = p.resident ? static_cast<uint32_t>(total_tiles)
-                                      : (n_images < static_cast<uint32_t>(p.stages - 1) ? n_images : p.stages - 1);
-    for (uint32_t i = 0; i < first; ++i) load_image(i);
-  }
 
-  {
-    const int slot = warp / kSlotWarps;
-    if (slot < tpc) {
-      // ========================================= slot warps ===================================================
-      const int wt = warp % kSlotWarps;
-      const int q = wt & 3;   // TMEM lane quarter of the scan
-      const int h = wt >> 2;  // which 64 columns of each unit this thread scans
-      const int scan_row = q * 32 + lane;
-      const uint32_t acc_col = tmem_base + slot * kNTile;
-      const uint32_t acc_addr = acc_col + (static_cast<uint32_t>(q * 32) << 16);
-      const uint32_t a_hi = ptx::smem_u32(s_a + slot * p.a_bytes);
-      const uint32_t a_lo = a_hi + p.a_bytes / 2;
-      const uint32_t ones = ptx::smem_u32(s_ones);
-      const uint32_t bar_u0 = ptx::smem_u32(&bar_unit[2 * slot]), bar_u1 = ptx::smem_u32(&bar_unit[2 * slot + 1]);
-      uint2* cand = reinterpret_cast<uint2*>(s_cand) + slot * 2 * kTileRows;  // [half][row] = (max bits, column)
-      const uint32_t bar_scan = 1 + slot, bar_issue = 1 + kSlots + slot;      // named barriers of this slot
-      // row-cooperative coordinates
-      const int j = lane % L::RPI, kc = lane / L::RPI;
-      const int rc_row0 = 16 * wt + j;  // + g * RPI
-      const bool want_loss = a.loss != nullptr || a.level_loss != nullptr;
-      uint32_t unit_phase = 0;
-      uint32_t it = 0;  // operand images consumed so far (ring position in streamed mode)
+  if (warp < kGroupWarps) {
+    // =========================================== row group ====================================================
+    ptx::setmaxnreg_inc<kRowRegs>();
+    const int slot = warp / WPS;
+    const int ws = warp % WPS;  // warp inside the sub-group
+    const uint32_t n_images = static_cast<uint32_t>(my_groups) * total_tiles;
+    auto load_image = [&](uint32_t i) {  // image i of this CTA's sequence -> its stage (one thread)
+      const int s = p.resident ? static_cast<int>(i) : static_cast<int>(i % p.stages);
+      const uint32_t bar = ptx::smem_u32(&bar_b_full[s]);
+      ptx::mbar_arrive_expect_tx(bar, p.tile_bytes);
+      ptx::bulk_g2s(ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes),
+                    p.packed + static_cast<size_t>(i % total_tiles) * p.tile_bytes, p.tile_bytes, bar);
+    };
+    if (threadIdx.x == 0) {
+      // resident: every image once; streamed: fill all stages but one (slot 0's issuer adds one image per iteration)
+      const uint32_t first = p.resident ? static_cast<uint32_t>(total_tiles)
+                                        : (n_images < static_cast<uint32_t>(p.stages - 1) ? n_images : p.stages - 1);
+      for (uint32_t i = 0; i < first; ++i) load_image(i);
+    }
+    const int j = lane % L::RPI, kc = lane / L::RPI;
+    const int rc_row0 = ws * (RPT * L::RPI) + j;  // + g * RPI
+    const uint32_t ones = ptx::smem_u32(s_ones);
+    const uint32_t a_hi = ptx::smem_u32(s_a + slot * p.a_bytes);
+    const uint32_t a_lo = a_hi + p.a_bytes / 2;
+    const uint32_t bar_slot = 1 + slot;  // named barrier of the sub-group
+    const uint32_t bar_scan = ptx::smem_u32(&bar_scan_done[slot]);
+    const uint32_t turn_addr = ptx::smem_u32(s_turn);
+    const uint2* cand = reinterpret_cast<const uint2*>(s_cand + slot * kCandSlotBytes);  // [half][row]
+    float* my_loss = s_loss + slot * kTileRows;
+    const bool want_loss = a.loss != nullptr || a.level_loss != nullptr;
+    // the last level's code row is only needed when something other than ids is asked for
+    const bool tail_last = a.emb_out != nullptr || want_loss || a.final_residual != nullptr;
+    uint32_t scan_phase = 0;
 
-      for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int64_t tile_row0 = (tpc * grp + slot) * kTileRows;  // may lie beyond n: the slot then runs on zeros
-        if (threadIdx.x % kSlotThreads == 0) {  // pull the slot's next row tile into L2 while this one is processed
-          const int64_t next_row0 = tile_row0 + static_cast<int64_t>(gridDim.x) * tpc * kTileRows;
-          if (next_row0 < a.n) {
-            const int64_t rows = a.n - next_row0 < kTileRows ? a.n - next_row0 : kTileRows;
-            ptx::bulk_prefetch_l2(a.x + next_row0 * D, static_cast<uint32_t>(rows * D * 4));
-          }
+    for (int k = 0; k < my_groups; ++k) {
+      const int64_t row0 = tile_row0(k, slot);
+      if (ws == 0 && lane == 0 && k + 1 < my_groups) {  // pull the slot's next row tile into L2
+        const int64_t next0 = tile_row0(k + 1, slot);
+        if (next0 < a.n) {
+          const int64_t rows = a.n - next0 < kTileRows ? a.n - next0 : kTileRows;
+          ptx::bulk_prefetch_l2(a.x + next0 * D, static_cast<uint32_t>(rows * D * 4));
         }
-        float r[L::RPT][8];
-        float total_loss[L::RPT];
+      }
+      float r[RPT][8];
 #pragma unroll
-        for (int g = 0; g < L::RPT; ++g) {
-          const int64_t grow = tile_row0 + rc_row0 + g * L::RPI;
-          total_loss[g] = 0.f;
-          if (grow < a.n) {
-            const float4* src = reinterpret_cast<const float4*>(a.x + grow * D + kc * 8);
-            const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
-            r[g][0] = v0.x, r[g][1] = v0.y, r[g][2] = v0.z, r[g][3] = v0.w;
-            r[g][4] = v1.x, r[g][5] = v1.y, r[g][6] = v1.z, r[g][7] = v1.w;
-          } else {
+      for (int g = 0; g < RPT; ++g) {
+        const int64_t grow = row0 + rc_row0 + g * L::RPI;
+        if (grow < a.n) {
+          const float4* src = reinterpret_cast<const float4*>(a.x + grow * D + kc * 8);
+          const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+          r[g][0] = v0.x, r[g][1] = v0.y, r[g][2] = v0.z, r[g][3] = v0.w;
+          r[g][4] = v1.x, r[g][5] = v1.y, r[g][6] = v1.z, r[g][7] = v1.w;
+        } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) r[g][i] = 0.f;
-          }
+          for (int i = 0; i < 8; ++i) r[g][i] = 0.f;
         }
+        if (want_loss && kc == 0) my_loss[rc_row0 + g * L::RPI] = 0.f;
+      }
 
-        for (int l = 0; l < a.n_levels; ++l) {
-          // ---- stage the residual as the A operand (bf16 hi | lo), optionally store it ----
+      for (int l = 0; l < n_levels; ++l) {
+        // ---- stage the residual as the A operand (bf16 hi | lo), optionally store it ----
 #pragma unroll
-          for (int g = 0; g < L::RPT; ++g) {
-            const int row = rc_row0 + g * L::RPI;
-            uint4 hi, lo;
-            split8(r[g], hi, lo);
-            sts128(a_hi + kc * (kTileRows * 16) + row * 16, hi);
-            sts128(a_lo + kc * (kTileRows * 16) + row * 16, lo);
-            if (a.residuals != nullptr) {
-              const int64_t grow = tile_row0 + row;
-              if (grow < a.n) {
-                float4* dst = reinterpret_cast<float4*>(a.residuals + (static_cast<int64_t>(l) * a.n + grow) * D + kc * 8);
-                dst[0] = make_float4(r[g][0], r[g][1], r[g][2], r[g][3]);
-                dst[1] = make_float4(r[g][4], r[g][5], r[g][6], r[g][7]);
-              }
-            }
-          }
-          ptx::fence_proxy_async_smem();
-
-          float best = -INFINITY;
-          int best_col = 0;
-          for (int t = 0; t < p.n_ktiles; ++t, ++it) {
-            // ---- slot barrier: A staged (t == 0) / accumulator drained (t > 0); warp 0 of the slot issues ----
-            ptx::tc_fence_before_sync();
-            if (wt == 0) {
-              ptx::named_bar_sync(bar_issue, kSlotThreads);
-              const int s = p.resident ? l * p.n_ktiles + t : static_cast<int>(it % p.stages);
-              const uint32_t b_phase = p.resident ? 0u : (it / p.stages) & 1u;
-              ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), b_phase);
-              ptx::tc_fence_after_sync();
-              if (ptx::elect_one()) {
-                const uint32_t b_tile = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
-                issue_unit<D>(acc_col, a_hi, a_lo, ones, b_tile, 0, bar_u0);
-                issue_unit<D>(acc_col + kUnitCols, a_hi, a_lo, ones, b_tile, kUnitCols, bar_u1);
-                if (!p.resident) {
-                  ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
-                  if (slot == 0) {
-                    // refill: image it + stages - 1 goes where image it - 1 was, once every slot's MMAs on it are done
-                    const uint32_t nxt = it + p.stages - 1;
-                    if (nxt < n_images) {
-                      if (it > 0) {
-                        const uint32_t prev = it - 1;
-                        ptx::mbar_wait(ptx::smem_u32(&bar_b_empty[prev % p.stages]), (prev / p.stages) & 1u);
-                      }
-                      load_image(nxt);
-                    }
-                  }
-                }
-              }
-              __syncwarp();
-            } else {
-              ptx::named_bar_arrive(bar_issue, kSlotThreads);
-            }
-            // ---- scan ----
-            float m;
-            int col;
-            scan_accumulator(acc_addr, h, bar_u0, bar_u1, unit_phase, tile_row0 + scan_row < a.n, m, col);
-            unit_phase ^= 1;
-            if (m > best) {  // strict: an earlier image keeps exact ties
-              best = m;
-              best_col = t * kNTile + col;
-            }
-          }
-          cand[h * kTileRows + scan_row] = make_uint2(__float_as_uint(best), static_cast<uint32_t>(best_col));
-          ptx::tc_fence_before_sync();
-          ptx::named_bar_sync(bar_scan, kSlotThreads);
-
-          // ---- row work: combine the two halves, gather the code row, value / loss / next residual ----
-          const float* cb = a.codebooks + static_cast<int64_t>(l) * a.k * D;
-          float e[L::RPT][8];
-          int idx[L::RPT];
-#pragma unroll
-          for (int g = 0; g < L::RPT; ++g) {
-            const int row = rc_row0 + g * L::RPI;
-            const uint2 c0 = cand[row], c1 = cand[kTileRows + row];
-            const float m0 = __uint_as_float(c0.x), m1 = __uint_as_float(c1.x);
-            const bool first = m0 > m1 || (m0 == m1 && c0.y < c1.y);  // lowest column wins exact ties
-            int k_sel = static_cast<int>(first ? c0.y : c1.y);
-            k_sel = k_sel < a.k ? k_sel : a.k - 1;
-            idx[g] = k_sel;
-            const float4* src = reinterpret_cast<const float4*>(cb + static_cast<int64_t>(k_sel) * D + kc * 8);
-            const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
-            e[g][0] = v0.x, e[g][1] = v0.y, e[g][2] = v0.z, e[g][3] = v0.w;
-            e[g][4] = v1.x, e[g][5] = v1.y, e[g][6] = v1.z, e[g][7] = v1.w;
-          }
-#pragma unroll
-          for (int g = 0; g < L::RPT; ++g) {
-            const int64_t grow = tile_row0 + rc_row0 + g * L::RPI;
-            const bool valid = grow < a.n;
-            float o[8];
-            float ll = 0.f;
-            if (want_loss) {
-              float s = 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float df = r[g][i] - e[g][i];
-                s = fmaf(df, df, s);
-              }
-              s = row_sum<D>(s);
-              ll = s + a.beta * s;  // (modules/loss.py:41-44)
-            }
-            if constexpr (!ROT) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = e[g][i];
-            } else {
-              // modules/quantize.py:34-45,134-140:  o = r - 2 (r.w) w + 2 (r.u) q
-              float rr = 0.f, ee = 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                rr = fmaf(r[g][i], r[g][i], rr);
-                ee = fmaf(e[g][i], e[g][i], ee);
-              }
-              rr = row_sum<D>(rr);
-              ee = row_sum<D>(ee);
-              const float inv_r = 1.0f / (sqrtf(rr) + 1e-8f);  // u = r / (|r| + 1e-8)
-              const float inv_e = 1.0f / (sqrtf(ee) + 1e-8f);  // q = e / (|e| + 1e-8)
-              float ss = 0.f, ru = 0.f, rs = 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float u = r[g][i] * inv_r;
-                const float qv = e[g][i] * inv_e;
-                const float s = u + qv;
-                ss = fmaf(s, s, ss);
-                ru = fmaf(r[g][i], u, ru);
-                rs = fmaf(r[g][i], s, rs);
-              }
-              ss = row_sum<D>(ss);
-              ru = row_sum<D>(ru);
-              rs = row_sum<D>(rs);
-              const float inv_s = 1.0f / fmaxf(sqrtf(ss), 1e-6f);  // w = (u+q) / max(|u+q|, 1e-6)
-              const float rw2 = 2.0f * (rs * inv_s);               // 2 (r.w)
-              const float ru2 = 2.0f * ru;                         // 2 (r.u)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float u = r[g][i] * inv_r;
-                const float qv = e[g][i] * inv_e;
-                const float w = (u + qv) * inv_s;
-                o[i] = r[g][i] - rw2 * w + ru2 * qv;
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r[g][i] = r[g][i] - o[i];
-            total_loss[g] += ll;
-            if (valid) {
-              if (a.emb_out != nullptr) {
-                float4* dst = reinterpret_cast<float4*>(a.emb_out + (static_cast<int64_t>(l) * a.n + grow) * D + kc * 8);
-                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-              }
-              if (kc == 0) {
-                a.ids[grow * a.ids_row_stride + l * a.ids_level_stride] = idx[g];
-                if (a.level_loss != nullptr) a.level_loss[static_cast<int64_t>(l) * a.n + grow] = ll;
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < L::RPT; ++g) {
-          const int64_t grow = tile_row0 + rc_row0 + g * L::RPI;
-          if (grow < a.n) {
-            if (kc == 0 && a.loss != nullptr) a.loss[grow] = total_loss[g];
-            if (a.final_residual != nullptr) {
-              float4* dst = reinterpret_cast<float4*>(a.final_residual + grow * D + kc * 8);
+        for (int g = 0; g < RPT; ++g) {
+          const int row = rc_row0 + g * L::RPI;
+          uint4 hi, lo;
+          split8(r[g], hi, lo);
+          sts128(a_hi + kc * (kTileRows * 16) + row * 16, hi);
+          sts128(a_lo + kc * (kTileRows * 16) + row * 16, lo);
+          if (a.residuals != nullptr) {
+            const int64_t grow = row0 + row;
+            if (grow < a.n) {
+              float4* dst = reinterpret_cast<float4*>(a.residuals + (static_cast<int64_t>(l) * a.n + grow) * D + kc * 8);
               dst[0] = make_float4(r[g][0], r[g][1], r[g][2], r[g][3]);
               dst[1] = make_float4(r[g][4], r[g][5], r[g][6], r[g][7]);
             }
           }
         }
+        ptx::fence_proxy_async_smem();
+        if (ws == 0) {
+          ptx::named_bar_sync(bar_slot, TPS);
+          // ---- issue the level's MMAs, one accumulator per operand image, in round-robin order over the slots ----
+          for (int t = 0; t < n_k; ++t) {
+            const uint32_t it = static_cast<uint32_t>((k * n_levels + l) * n_k + t);  // image index in this CTA's sequence
+            const uint32_t s_issue = it * NSLOT + slot;                               // accumulator sequence number
+            const uint32_t acc = s_issue & 1u;
+            if (NSLOT > 1) ptx::counter_wait(turn_addr, s_issue);
+            ptx::mbar_wait(ptx::smem_u32(&bar_acc_free[acc]), ((s_issue >> 1) & 1u) ^ 1u);
+            const int s = p.resident ? l * n_k + t : static_cast<int>(it % p.stages);
+            ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), p.resident ? 0u : (it / p.stages) & 1u);
+            ptx::tc_fence_after_sync();
+            if (ptx::elect_one()) {
+              const uint32_t b_tile = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
+              const uint32_t acc_col = tmem_base + acc * kNTile;
+              issue_unit<D>(acc_col, a_hi, a_lo, ones, b_tile, 0, ptx::smem_u32(&bar_mma_done[2 * acc]));
+              issue_unit<D>(acc_col + kUnitCols, a_hi, a_lo, ones, b_tile, kUnitCols, ptx::smem_u32(&bar_mma_done[2 * acc + 1]));
+              if (NSLOT > 1) ptx::counter_add_release(turn_addr, 1);
+              if (!p.resident) {
+                ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
+                if (slot == 0) {
+                  // refill: image it + stages - 1 goes where image it - 1 was, once every slot's MMAs on it are done
+                  const uint32_t nxt = it + p.stages - 1;
+                  if (nxt < n_images) {
+                    if (it > 0) {
+                      const uint32_t prev = it - 1;
+                      ptx::mbar_wait(ptx::smem_u32(&bar_b_empty[prev % p.stages]), (prev / p.stages) & 1u);
+                    }
+                    load_image(nxt);
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          }
+        } else {
+          ptx::named_bar_arrive(bar_slot, TPS);
+        }
+
+        // ---- wait for the scan, merge the two halves of every row, write ids, gather, value / loss / residual ----
+        ptx::mbar_wait(bar_scan, scan_phase);
+        scan_phase ^= 1;
+        const float* cb = a.codebooks + static_cast<int64_t>(l) * a.k * D;
+        const bool last = l + 1 == n_levels;
+        const bool tail = !last || tail_last;
+#pragma unroll
+        for (int g0 = 0; g0 < RPT; g0 += GC) {
+          float e[GC][8];
+#pragma unroll
+          for (int gg = 0; gg < GC; ++gg) {
+            const int row = rc_row0 + (g0 + gg) * L::RPI;
+            const uint2 c0 = cand[row], c1 = cand[kTileRows + row];
+            const float m0 = __uint_as_float(c0.x), m1 = __uint_as_float(c1.x);
+            const bool first = m0 > m1 || (m0 == m1 && c0.y < c1.y);  // lowest column wins exact ties
+            uint32_t k_sel = first ? c0.y : c1.y;
+            k_sel = k_sel < static_cast<uint32_t>(a.k) ? k_sel : static_cast<uint32_t>(a.k - 1);
+            const int64_t grow = row0 + row;
+            if (kc == 0 && grow < a.n) a.ids[grow * a.ids_row_stride + l * a.ids_level_stride] = k_sel;
+            if (tail) {
+              const float4* src = reinterpret_cast<const float4*>(cb + static_cast<int64_t>(k_sel) * D + kc * 8);
+              const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+              e[gg][0] = v0.x, e[gg][1] = v0.y, e[gg][2] = v0.z, e[gg][3] = v0.w;
+              e[gg][4] = v1.x, e[gg][5] = v1.y, e[gg][6] = v1.z, e[gg][7] = v1.w;
+            }
+          }
+          if (tail) {
+#pragma unroll
+            for (int gg = 0; gg < GC; ++gg) {
+              const int g = g0 + gg;
+              const int row = rc_row0 + g * L::RPI;
+              const int64_t grow = row0 + row;
+              const bool valid = grow < a.n;
+              float o[8];
+              float ll = 0.f;
+              if (want_loss) {
+                float sq = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float df = r[g][i] - e[gg][i];
+                  sq = fmaf(df, df, sq);
+                }
+                sq = row_sum<D>(sq);
+                ll = sq + a.beta * sq;  // (modules/loss.py:41-44)
+              }
+              if constexpr (!ROT) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = e[gg][i];
+              } else {
+                // modules/quantize.py:34-45,134-140:  o = r - 2 (r.w) w + 2 (r.u) q
+                float rr = 0.f, ee = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  rr = fmaf(r[g][i], r[g][i], rr);
+                  ee = fmaf(e[gg][i], e[gg][i], ee);
+                }
+                rr = row_sum<D>(rr);
+                ee = row_sum<D>(ee);
+                const float inv_r = 1.0f / (sqrtf(rr) + 1e-8f);  // u = r / (|r| + 1e-8)
+                const float inv_e = 1.0f / (sqrtf(ee) + 1e-8f);  // q = e / (|e| + 1e-8)
+                float ss = 0.f, ru = 0.f, rs = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float u = r[g][i] * inv_r;
+                  const float qv = e[gg][i] * inv_e;
+                  const float sv = u + qv;
+                  ss = fmaf(sv, sv, ss);
+                  ru = fmaf(r[g][i], u, ru);
+                  rs = fmaf(r[g][i], sv, rs);
+                }
+                ss = row_sum<D>(ss);
+                ru = row_sum<D>(ru);
+                rs = row_sum<D>(rs);
+                const float inv_s = 1.0f / fmaxf(sqrtf(ss), 1e-6f);  // w = (u+q) / max(|u+q|, 1e-6)
+                const float rw2 = 2.0f * (rs * inv_s);               // 2 (r.w)
+                const float ru2 = 2.0f * ru;                         // 2 (r.u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float u = r[g][i] * inv_r;
+                  const float qv = e[gg][i] * inv_e;
+                  const float w = (u + qv) * inv_s;
+                  o[i] = r[g][i] - rw2 * w + ru2 * qv;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[g][i] = r[g][i] - o[i];
+              if (valid && a.emb_out != nullptr) {
+                float4* dst = reinterpret_cast<float4*>(a.emb_out + (static_cast<int64_t>(l) * a.n + grow) * D + kc * 8);
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+              }
+              if (want_loss && kc == 0) {
+                const float tot = my_loss[row] + ll;  // private to this thread
+                my_loss[row] = tot;
+                if (valid) {
+                  if (a.level_loss != nullptr) a.level_loss[static_cast<int64_t>(l) * a.n + grow] = ll;
+                  if (last && a.loss != nullptr) a.loss[grow] = tot;
+                }
+              }
+              if (last && valid && a.final_residual != nullptr) {
+                float4* dst = reinterpret_cast<float4*>(a.final_residual + grow * D + kc * 8);
+                dst[0] = make_float4(r[g][0], r[g][1], r[g][2], r[g][3]);
+                dst[1] = make_float4(r[g][4], r[g][5], r[g][6], r[g][7]);
+              }
+            }
+          }
+        }
       }
-    }  // else: slot without row tiles (small N: one tile per CTA so that more SMs work)
+    }
+  } else {
+    // =========================================== scan group ===================================================
+    ptx::setmaxnreg_dec<kScanRegs>();
+    const int sw = warp - kGroupWarps;
+    const int q = sw & 3;   // TMEM lane quarter
+    const int h = sw >> 2;  // which 64 columns of each unit this thread scans
+    const int scan_row = q * 32 + lane;
+    uint32_t s = 0;  // accumulators scanned so far
+    for (int k = 0; k < my_groups; ++k) {
+      for (int lt = 0; lt < total_tiles; ++lt) {
+        const int t = lt % n_k;
+#pragma unroll 1
+        for (int slot = 0; slot < NSLOT; ++slot, ++s) {
+          const uint32_t acc = s & 1u, par = (s >> 1) & 1u;
+          const uint32_t acc_addr = tmem_base + acc * kNTile + (static_cast<uint32_t>(q * 32) << 16);
+          float m;
+          int col;
+          scan_accumulator(acc_addr, h, ptx::smem_u32(&bar_mma_done[2 * acc]), ptx::smem_u32(&bar_mma_done[2 * acc + 1]), par,
+                           tile_row0(k, slot) + scan_row < a.n, m, col);
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_acc_free[acc]));
+          // running (max, column) over the level's operand images lives in the thread's own candidate entry
+          uint2* c = reinterpret_cast<uint2*>(s_cand + slot * kCandSlotBytes) + h * kTileRows + scan_row;
+          col += t * kNTile;
+          if (t > 0) {
+            const uint2 prev = *c;
+            if (!(m > __uint_as_float(prev.x))) {  // strict: an earlier image keeps exact ties
+              m = __uint_as_float(prev.x);
+              col = static_cast<int>(prev.y);
+            }
+          }
+          *c = make_uint2(__float_as_uint(m), static_cast<uint32_t>(col));
+          if (t == n_k - 1) {
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_scan_done[slot]));
+          }
+        }
+      }
+    }
   }
 
   ptx::tc_fence_before_sync();
@@ -626,6 +696,28 @@ int pack_d(const float* codebooks, int n_levels, int k, const TcPlan& plan, uint
   return HV_OK;
 }
 
+template <int D, int NSLOT>
+int launch_slots(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, const DeviceProps& props, cudaStream_t stream) {
+  const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
+  const int64_t n_groups = (n_row_tiles + NSLOT - 1) / NSLOT;
+  const unsigned grid = static_cast<unsigned>(n_groups < props.sm_count ? n_groups : props.sm_count);
+  TcParams p{packed, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes};
+  auto go = [&](auto kernel) -> int {
+    cudaFuncAttributes attr;
+    HV_CUDA_CHECK(cudaFuncGetAttributes(&attr, kernel));
+    if (attr.numRegs * 2 < kRowRegs + kScanRegs) {  // setmaxnreg.inc would wait forever: refuse loudly instead
+      set_error("hv_rq_forward: tcgen05 kernel was built with %d registers/thread, the register hand-over needs %d",
+                attr.numRegs, (kRowRegs + kScanRegs) / 2);
+      return HV_ERR_UNSUPPORTED;
+    }
+    HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    kernel<<<grid, kThreads, plan.smem_bytes, stream>>>(a, p);
+    HV_CUDA_CHECK(cudaGetLastError());
+    return HV_OK;
+  };
+  return rot ? go(rq_fwd_tc_kernel<D, true, NSLOT>) : go(rq_fwd_tc_kernel<D, false, NSLOT>);
+}
+
 template <int D>
 int launch_d(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, bool prepacked, cudaStream_t stream) {
   if (!prepacked)
@@ -633,18 +725,18 @@ int launch_d(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, 
   DeviceProps props;
   if (int st = device_props(&props)) return st;
   const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
-  // two row tiles per CTA as soon as one per SM does not cover them
-  const int tpc = n_row_tiles > props.sm_count ? kSlots : 1;
-  const int64_t n_groups = (n_row_tiles + tpc - 1) / tpc;
-  const unsigned grid = static_cast<unsigned>(n_groups < props.sm_count ? n_groups : props.sm_count);
-  TcParams p{packed, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes, tpc};
-  auto go = [&](auto kernel) -> int {
-    HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-    kernel<<<grid, kThreads, plan.smem_bytes, stream>>>(a, p);
-    HV_CUDA_CHECK(cudaGetLastError());
-    return HV_OK;
-  };
-  return rot ? go(rq_fwd_tc_kernel<D, true>) : go(rq_fwd_tc_kernel<D, false>);
+  // as many row tiles in flight per CTA as it takes to cover them with one CTA per SM (1, 2 or Cfg<D>::NT)
+  const int64_t per_sm = (n_row_tiles + props.sm_count - 1) / props.sm_count;
+  static const int forced = [] {
+    const char* e = getenv("HIDVAE_TC_SLOTS");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  int nslot = per_sm <= 1 ? 1 : (per_sm == 2 ? 2 : Cfg<D>::NT);
+  if (forced == 1 || forced == 2 || (forced == 4 && Cfg<D>::NT == 4)) nslot = forced;  // tuning experiments only
+  if constexpr (Cfg<D>::NT == 4)
+    if (nslot == 4) return launch_slots<D, 4>(a, rot, plan, packed, props, stream);
+  return nslot == 1 ? launch_slots<D, 1>(a, rot, plan, packed, props, stream)
+                    : launch_slots<D, 2>(a, rot, plan, packed, props, stream);
 }
 
 bool use_v4() {
