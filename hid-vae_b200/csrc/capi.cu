@@ -67,8 +67,8 @@ int hv_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 size_t hv_workspace_bytes(int op, int64_t n, int d, int k, int n_levels) {
-  (void)n;
   if (op == HV_OP_RQ_FORWARD) return hv::rq_fwd_tc_workspace_bytes(d, k, n_levels);
+  if (op == HV_OP_RQ_BACKWARD && n > 0 && d > 0 && k > 0 && n_levels > 0) return hv::rq_bwd_workspace_bytes(n, d, k, n_levels);
   return 0;
 }
 

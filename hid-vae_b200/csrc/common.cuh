@@ -59,6 +59,7 @@ int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* wor
 int launch_rq_fwd_tc_v4(const RqFwdArgs& a, int d, bool rot, void* packed, cudaStream_t stream);
 bool rq_fwd_tc_supported(int d, int k, int n_levels);
 size_t rq_fwd_tc_workspace_bytes(int d, int k, int n_levels);
+size_t rq_bwd_workspace_bytes(int64_t n, int d, int k, int n_levels);
 
 // ---------------------------------------------------------------------------------------------------------
 // Per-row "tail" of one quantiser level: everything after the argmin.  One thread owns one row in registers.

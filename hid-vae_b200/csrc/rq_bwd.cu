@@ -11,6 +11,8 @@
 // The codebook gradient is a scatter-add by id (the embedding_dense_backward of modules/quantize.py:97-98):
 // when [L, K, D] fits, it is accumulated with shared-memory atomics per CTA and flushed once, otherwise (or for
 // small N) with global red.add.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hv {
@@ -38,6 +40,9 @@ struct RqBwdArgs {
   const float* g_level_loss;
   float* g_x;
   float* g_codebooks;
+  int debug;  // HIDVAE_BWD_DEBUG ablation mask (timing experiments only)
+  float* replicas;    // [n_replicas, L, K, D] zeroed scratch or null: CTAs spread their reductions over the copies
+  int n_replicas;
 };
 
 template <int LPR>
@@ -76,6 +81,7 @@ __global__ void __launch_bounds__(kBwdThreads, LMAX <= 4 ? 3 : 1) rq_bwd_kernel(
   const int n_warps = (gridDim.x * kBwdThreads) >> 5;
   const int64_t n_groups = (a.n + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
   const bool rot = ROT && a.training;
+  float* gc_base = a.n_replicas > 0 ? a.replicas + static_cast<int64_t>(blockIdx.x % a.n_replicas) * lkd : a.g_codebooks;
 
   for (int64_t g = warp_global; g < n_groups; g += n_warps) {
     const int64_t row = g * ROWS_PER_WARP + lane / LPR;
@@ -92,6 +98,7 @@ __global__ void __launch_bounds__(kBwdThreads, LMAX <= 4 ? 3 : 1) rq_bwd_kernel(
         int64_t code = a.ids[rrow * a.ids_row_stride + l * a.ids_level_stride];
         code = code < 0 ? 0 : (code >= a.k ? a.k - 1 : code);
         id[l] = static_cast<int>(code);
+        if (a.debug & 2) code = (row + 7 * l) & (a.k - 1);
         const float4 e = __ldg(reinterpret_cast<const float4*>(a.codebooks + (static_cast<int64_t>(l) * a.k + code) * D) + sub);
         R[l] = r;
         E[l] = e;
@@ -119,18 +126,28 @@ __global__ void __launch_bounds__(kBwdThreads, LMAX <= 4 ? 3 : 1) rq_bwd_kernel(
       }
     }
 
+    // every load of the row is issued before the recursion (the red.add below orders memory, so nothing can be
+    // hoisted across it by the compiler): one latency exposure per row instead of one per level
     const float gl_all = a.g_loss != nullptr ? a.g_loss[rrow * a.g_loss_stride] : 0.f;
+    float4 GE[LMAX];
+    float GL[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      GE[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+      GL[l] = gl_all;
+      if (l < a.n_levels) {
+        if (a.g_emb != nullptr)
+          GE[l] = __ldg(reinterpret_cast<const float4*>(a.g_emb + l * a.g_emb_level_stride + rrow * a.g_emb_row_stride) + sub);
+        if (a.g_level_loss != nullptr) GL[l] += a.g_level_loss[static_cast<int64_t>(l) * a.n + rrow];
+      }
+    }
     float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int l = LMAX - 1; l >= 0; --l) {
       if (l < a.n_levels) {
-        float gl = gl_all;
-        if (a.g_level_loss != nullptr) gl += a.g_level_loss[static_cast<int64_t>(l) * a.n + rrow];
-        float4 h = make_float4(-G.x, -G.y, -G.z, -G.w);
-        if (a.g_emb != nullptr) {
-          const float4 ge = __ldg(reinterpret_cast<const float4*>(a.g_emb + l * a.g_emb_level_stride + rrow * a.g_emb_row_stride) + sub);
-          h.x += ge.x, h.y += ge.y, h.z += ge.z, h.w += ge.w;
-        }
+        const float gl = GL[l];
+        const float4 ge = GE[l];
+        float4 h = make_float4(ge.x - G.x, ge.y - G.y, ge.z - G.z, ge.w - G.w);
         const float4 rl = R[l], el = E[l];
         const float4 diff = make_float4(rl.x - el.x, rl.y - el.y, rl.z - el.z, rl.w - el.w);
         const float c2 = 2.0f * gl;
@@ -165,7 +182,7 @@ __global__ void __launch_bounds__(kBwdThreads, LMAX <= 4 ? 3 : 1) rq_bwd_kernel(
             atomicAdd(dst + 2, ge_code.z);
             atomicAdd(dst + 3, ge_code.w);
           } else {
-            red_add_v4(a.g_codebooks + off, ge_code);
+            if (!(a.debug & 1)) red_add_v4(gc_base + off, ge_code);
           }
         }
       }
@@ -207,14 +224,41 @@ int launch_d(const RqBwdArgs& a, bool rot, cudaStream_t stream) {
   return rot ? go(rq_bwd_kernel<D, true, false, kMaxLevels>, 0) : go(rq_bwd_kernel<D, false, false, kMaxLevels>, 0);
 }
 
+// g_codebooks += sum over the replicas (they were zeroed before the main kernel ran)
+__global__ void rq_bwd_fold_replicas_kernel(const float* __restrict__ replicas, int n_replicas, int64_t lkd4,
+                                            float* __restrict__ g_codebooks) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= lkd4) return;
+  float4 acc = reinterpret_cast<float4*>(g_codebooks)[i];
+  for (int r = 0; r < n_replicas; ++r) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(replicas) + r * lkd4 + i);
+    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  }
+  reinterpret_cast<float4*>(g_codebooks)[i] = acc;
+}
+
 }  // namespace
+
+// Replicas of the [L, K, D] gradient the CTAs spread their red.add over: the L2 atomic units serialise per address,
+// and with 768 hot lines (K = 256, D = 32, L = 3) that serialisation was 40 % of the kernel (profiles/README.md).
+int rq_bwd_replicas(int64_t n, int d, int k, int n_levels) {
+  const int64_t lkd_bytes = static_cast<int64_t>(n_levels) * k * d * 4;
+  if (n < 32768 || lkd_bytes <= 0) return 0;
+  int64_t r = (32ll << 20) / lkd_bytes;  // at most 32 MiB of scratch
+  r = r > 32 ? 32 : r;
+  return r < 2 ? 0 : static_cast<int>(r);
+}
+size_t rq_bwd_workspace_bytes(int64_t n, int d, int k, int n_levels) {
+  return static_cast<size_t>(rq_bwd_replicas(n, d, k, n_levels)) * n_levels * k * d * 4;
+}
 }  // namespace hv
 
 extern "C" int hv_rq_backward(const float* x, int64_t n, int d, const float* codebooks, int n_levels, int k, int mode,
                               int training, float beta, const int64_t* ids, int64_t ids_row_stride,
                               int64_t ids_level_stride, const float* g_emb, int64_t g_emb_level_stride,
                               int64_t g_emb_row_stride, const float* g_loss, int64_t g_loss_stride,
-                              const float* g_level_loss, float* g_x, float* g_codebooks, void* stream) {
+                              const float* g_level_loss, float* g_x, float* g_codebooks, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   using namespace hv;
   if (n < 0 || d <= 0 || k <= 0 || n_levels <= 0) {
     set_error("hv_rq_backward: bad shape n=%lld d=%d k=%d L=%d", (long long)n, d, k, n_levels);
@@ -239,18 +283,36 @@ extern "C" int hv_rq_backward(const float* x, int64_t n, int d, const float* cod
     return HV_ERR_MISALIGNED;
   }
   RqBwdArgs a{x, codebooks, n, n_levels, k, beta, training ? 1 : 0, ids, ids_row_stride, ids_level_stride,
-              g_emb, g_emb_level_stride, g_emb_row_stride, g_loss, g_loss_stride, g_level_loss, g_x, g_codebooks};
+              g_emb, g_emb_level_stride, g_emb_row_stride, g_loss, g_loss_stride, g_level_loss, g_x, g_codebooks, 0, nullptr, 0};
+  {
+    static const int dbg = [] { const char* e = getenv("HIDVAE_BWD_DEBUG"); return e != nullptr ? atoi(e) : 0; }();
+    a.debug = dbg;
+  }
   const bool rot = mode == HV_MODE_ROTATION_TRICK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n_rep = rq_bwd_replicas(n, d, k, n_levels);
+  const size_t rep_bytes = rq_bwd_workspace_bytes(n, d, k, n_levels);
+  const bool use_rep = n_rep > 0 && workspace != nullptr && workspace_bytes >= rep_bytes && aligned16(workspace) && !(a.debug & 4);
+  if (use_rep) {
+    HV_CUDA_CHECK(cudaMemsetAsync(workspace, 0, rep_bytes, s));
+    a.replicas = static_cast<float*>(workspace);
+    a.n_replicas = n_rep;
+  }
+  int st;
   switch (d) {
-    case 4: return launch_d<4>(a, rot, s);
-    case 8: return launch_d<8>(a, rot, s);
-    case 16: return launch_d<16>(a, rot, s);
-    case 32: return launch_d<32>(a, rot, s);
-    case 64: return launch_d<64>(a, rot, s);
-    case 128: return launch_d<128>(a, rot, s);
+    case 4: st = launch_d<4>(a, rot, s); break;
+    case 8: st = launch_d<8>(a, rot, s); break;
+    case 16: st = launch_d<16>(a, rot, s); break;
+    case 32: st = launch_d<32>(a, rot, s); break;
+    case 64: st = launch_d<64>(a, rot, s); break;
+    case 128: st = launch_d<128>(a, rot, s); break;
     default:
       set_error("hv_rq_backward: embed dim %d has no instantiation (supported: 4, 8, 16, 32, 64, 128)", d);
       return HV_ERR_UNSUPPORTED;
   }
+  if (st != HV_OK || !use_rep) return st;
+  const int64_t lkd4 = static_cast<int64_t>(n_levels) * k * d / 4;
+  rq_bwd_fold_replicas_kernel<<<static_cast<unsigned>((lkd4 + 255) / 256), 256, 0, s>>>(a.replicas, n_rep, lkd4, g_codebooks);
+  HV_CUDA_CHECK(cudaGetLastError());
+  return HV_OK;
 }

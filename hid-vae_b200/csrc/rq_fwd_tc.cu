@@ -45,22 +45,30 @@ namespace {
 constexpr int kTileRows = 128;
 constexpr int kNTile = 256;                 // codes per operand image (= accumulator columns of a slot)
 constexpr int kUnitCols = 128;              // N of one tcgen05.mma
-constexpr int kSlotWarps = 8;               // a slot = 8 warps, one accumulator set, two row tiles in flight
-constexpr int kSlotThreads = kSlotWarps * 32;
+constexpr int kMaxSlots = 4;                // row tiles in flight per CTA (Cfg<D>::NT of them)
+constexpr int kGroupWarps = 8;              // warps of the row group == warps of the scan group
+constexpr int kThreads = 2 * kGroupWarps * 32;
+constexpr int kRowRegs = 160, kScanRegs = 96;  // setmaxnreg split of the 128-per-thread launch allocation
+static_assert(kRowRegs + kScanRegs == 256, "register hand-over must stay inside the launch allocation");
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 16;
 constexpr int kOnesBytes = 2 * kTileRows * 16;              // one K=16 step of the A operand: [2 chunks][128 rows][8 bf16]
 constexpr int kCandSlotBytes = 2 * kTileRows * 8;           // (max, column) per half, row of one slot
 constexpr int kLossSlotBytes = kTileRows * 4;               // running loss per row of one slot
-constexpr int kBarBytes = 1024;
+constexpr int kBarBytes = 4096;
 constexpr int kSmemLimit = 227 * 1024;
+#ifdef HV_TC_INSTRUMENT
+constexpr bool kAblate = true;   // HIDVAE_TC_DEBUG bits 1/2/4 drop the scan / the gather / the MMAs (timing experiments)
+#else
+constexpr bool kAblate = false;
+#endif
 
-// slots per CTA: two while four A operands (two row tiles per slot) fit beside the operand images, else one
+// row tiles in flight: four while their A operands fit beside the operand images, else two
 template <int D>
 struct Cfg {
-  static constexpr int NT = D <= 32 ? 2 : 1;
+  static constexpr int NT = D <= 32 ? 4 : 2;
 };
-inline int slots_for(int d) { return d <= 32 ? 2 : 1; }
+inline int slots_for(int d) { return d <= 32 ? 4 : 2; }
 
 struct TcPlan {
   int n_ktiles;    // operand images per level
@@ -68,7 +76,7 @@ struct TcPlan {
   int stages;      // shared-memory stages for images
   int resident;    // 1: every (level, image) has its own stage and is loaded once
   int smem_bytes;
-  int a_bytes;     // one row tile's A operand (hi + lo) == one fp32 row tile
+  int a_bytes;     // one slot's A operand (hi + lo) == one fp32 row tile
 };
 
 bool make_plan(int d, int k, int n_levels, TcPlan* p) {
@@ -76,7 +84,7 @@ bool make_plan(int d, int k, int n_levels, TcPlan* p) {
   p->n_ktiles = (k + kNTile - 1) / kNTile;
   p->tile_bytes = kNTile * (4 * d + 32);
   p->a_bytes = kTileRows * d * 4;
-  const int fixed = slots_for(d) * 2 * (p->a_bytes + kCandSlotBytes + kLossSlotBytes) + kOnesBytes + kBarBytes;
+  const int fixed = slots_for(d) * (p->a_bytes + kCandSlotBytes + kLossSlotBytes) + kOnesBytes + kBarBytes;
   const int budget = kSmemLimit - fixed;
   const long long total_tiles = static_cast<long long>(n_levels) * p->n_ktiles;
   if (total_tiles <= kMaxStages && total_tiles * p->tile_bytes <= budget) {
@@ -157,6 +165,7 @@ struct TcParams {
   int stages;
   int resident;
   int a_bytes;
+  int debug;  // HIDVAE_TC_DEBUG ablation mask (timing experiments only; results are then meaningless)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -328,52 +337,65 @@ __device__ __forceinline__ void scan_accumulator(uint32_t acc_addr, int h, uint3
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// The kernel.  A persistent CTA runs NSLOT independent "slots" of 8 warps; a slot owns one accumulator set in TMEM
-// and works on TWO row tiles at a time (A and B), alternating between them step by step:
+// The kernel: a pipeline between two warp groups of the persistent CTA, all hand-overs are mbarriers.
 //
-//   step(cur, oth):   scan(cur)            2-D fold argmax of cur's accumulator (waits for cur's MMAs, issued one
-//                                          step ago -- normally long finished)
-//                     slot barrier         cur's candidates visible, its accumulator drained
-//                     issue MMA(oth)       one elected thread; oth's A operand was staged in the previous step.  The
-//                                          tensor pipe works on oth while ...
-//                     row work(cur)        ... the slot merges cur's candidates, writes ids, gathers the chosen code
-//                                          rows, forms value / loss / next residual and stages cur's next A operand
-//                     swap(cur, oth)
-//
-//   so a slot never waits for its own MMAs, the only synchronisation is one named barrier per step, and the second
-//   slot (an independent instruction stream with its own accumulator) fills the issue slots the first leaves idle in
-//   its global-load latencies.  NACC = 2 (one slot, one accumulator per row tile; D = 64) issues MMA(oth) before
-//   scan(cur) instead, which keeps the tensor pipe busy back to back when the MMAs are the longer part.
+//   row group  (warps 0-7)   split in NSLOT sub-groups of 8 / NSLOT warps; a sub-group owns one row tile ("slot") at a
+//                            time in the row-cooperative layout and runs, per level:
+//                              stage the residual as the slot's A operand (bf16 hi | lo)  ->  its first warp issues the
+//                              level's tcgen05.mma into the next free accumulator (2 x 256 TMEM columns used
+//                              alternately; a turn counter keeps the sub-groups in round-robin order)  ->  wait for the
+//                              slot's scan  ->  merge the two half-row candidates, write the id, gather the chosen code
+//                              row  ->  value / loss / next residual.
+//                            The sub-groups are independent instruction streams, so one slot's global-load and MMA
+//                            latencies are covered by the others.
+//   scan group (warps 8-15)  takes the accumulators in issue order: 2-D fold argmax (scan_accumulator), candidate
+//                            (max, column) per half row into shared memory, scan_done[slot] / acc_free[acc].
 // ---------------------------------------------------------------------------------------------------------
-template <int D, bool ROT, int NSLOT, int NACC>
-__global__ void __launch_bounds__(NSLOT* kSlotThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcParams p) {
+template <int D, bool ROT, int NSLOT>
+__global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcParams p) {
   using L = Rc<D>;
-  constexpr int RPT = L::RPT;
-  static_assert(NSLOT * NACC <= 2, "two 256-column accumulators in TMEM");
+  constexpr int WPS = kGroupWarps / NSLOT;                 // warps per slot
+  constexpr int TPS = WPS * 32;                            // threads per slot
+  constexpr int RPT = kTileRows * L::KC / TPS;             // rows per thread
+  constexpr int GC = RPT < 4 ? RPT : 4;                    // rows gathered at a time
   extern __shared__ __align__(1024) uint8_t smem[];
-  // [A (slot, tile) x (hi | lo) ... | ones | candidates | loss | barriers | B stages ...]  (sized for slots_for(D))
+  // [A slot 0 (hi | lo) | ... | ones | candidates | loss | barriers | B stages ...]   (sized for kMaxSlots slots)
   constexpr int n_slots_smem = Cfg<D>::NT;
   uint8_t* s_a = smem;
-  uint8_t* s_ones = smem + n_slots_smem * 2 * p.a_bytes;
+  uint8_t* s_ones = smem + n_slots_smem * p.a_bytes;
   uint8_t* s_cand = s_ones + kOnesBytes;
-  float* s_loss = reinterpret_cast<float*>(s_cand + n_slots_smem * 2 * kCandSlotBytes);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cand + n_slots_smem * 2 * (kCandSlotBytes + kLossSlotBytes));
+  float* s_loss = reinterpret_cast<float*>(s_cand + n_slots_smem * kCandSlotBytes);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_cand + n_slots_smem * (kCandSlotBytes + kLossSlotBytes));
   uint8_t* s_b = reinterpret_cast<uint8_t*>(s_bar) + kBarBytes;
 
-  uint64_t* bar_b_full = s_bar;                     // [kMaxStages]  TMA -> MMA issuers
-  uint64_t* bar_b_empty = bar_b_full + kMaxStages;  // [kMaxStages]  MMA completion (one commit per slot) -> TMA
-  uint64_t* bar_unit = bar_b_empty + kMaxStages;    // [2 accumulators][2 units]  MMA completion -> scan
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_unit + 4);
+  uint64_t* bar_b_full = s_bar;                      // [kMaxStages]  TMA -> MMA issuers
+  uint64_t* bar_b_empty = bar_b_full + kMaxStages;   // [kMaxStages]  MMA completion (one commit per slot) -> TMA
+  uint64_t* bar_mma_done = bar_b_empty + kMaxStages; // [2 acc][2 units]  MMA completion -> scan group
+  uint64_t* bar_acc_free = bar_mma_done + 4;         // [2 acc]       scan group (8 warps) -> MMA issuers
+  uint64_t* bar_scan_done = bar_acc_free + 2;        // [kMaxSlots]   scan group (8 warps) -> the slot's sub-group
+  uint32_t* s_turn = reinterpret_cast<uint32_t*>(bar_scan_done + kMaxSlots);  // number of accumulators issued so far
+  uint32_t* s_tmem = s_turn + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  uint32_t* s_ts = s_tmem + 1;  // [2][384] timestamps (HIDVAE_TC_DEBUG & 64, block 0)
+  int ts_n = 0;
+#ifdef HV_TC_INSTRUMENT
+  const bool ts_on = (p.debug & 64) && blockIdx.x == 0 && lane == 0;
+#else
+  constexpr bool ts_on = false;  // make EXTRA=-DHV_TC_INSTRUMENT: clock64 timeline of block 0 (HIDVAE_TC_DEBUG & 64)
+#endif
+  auto stamp = [&](int who, int code) { if (ts_on && ts_n < 190) { s_ts[who * 384 + 2 * ts_n] = code; s_ts[who * 384 + 2 * ts_n + 1] = static_cast<uint32_t>(clock64()); ++ts_n; } };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_b_full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bar_b_empty[s]), NSLOT);
     }
-    for (int i = 0; i < 4; ++i) ptx::mbar_init(ptx::smem_u32(&bar_unit[i]), 1);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(ptx::smem_u32(&bar_mma_done[i]), 1);
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(ptx::smem_u32(&bar_acc_free[i]), kGroupWarps);
+    for (int i = 0; i < kMaxSlots; ++i) ptx::mbar_init(ptx::smem_u32(&bar_scan_done[i]), kGroupWarps);
+    *s_turn = 0;
     ptx::fence_mbar_init();
   }
   if (warp == 0) {
@@ -394,325 +416,318 @@ __global__ void __launch_bounds__(NSLOT* kSlotThreads, 1) rq_fwd_tc_kernel(RqFwd
   const uint32_t tmem_base = *s_tmem;
 
   const int n_levels = a.n_levels, n_k = p.n_ktiles;
-  const int total_tiles = n_levels * n_k;
   const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
   const int64_t n_groups = (n_row_tiles + NSLOT - 1) / NSLOT;  // a group = NSLOT consecutive row tiles, one per slot
-  const int G = static_cast<int>((n_groups - 1 - blockIdx.x) / gridDim.x + 1);  // groups of this CTA (grid <= n_groups)
-  // every slot walks the CTA's groups: tile A takes the even ones, tile B the odd ones; pair round P = images both see
-  const uint32_t n_images = static_cast<uint32_t>((G + 1) / 2) * total_tiles;
-
-  const int slot = warp / kSlotWarps;
-  const int wt = warp % kSlotWarps;
-  const int q = wt & 3;   // TMEM lane quarter of the scan
-  const int h = wt >> 2;  // which 64 columns of each unit this thread scans
-  const int scan_row = q * 32 + lane;
-  const int j = lane % L::RPI, kc = lane / L::RPI;  // row-cooperative coordinates
-  const int rc_row0 = 16 * wt + j;                  // + g * RPI
-  const uint32_t ones = ptx::smem_u32(s_ones);
-  const uint32_t a_base = ptx::smem_u32(s_a + slot * 2 * p.a_bytes);              // + x * a_bytes
-  const uint32_t cand_base = ptx::smem_u32(s_cand + slot * 2 * kCandSlotBytes);   // + x * kCandSlotBytes
-  float* loss_base = s_loss + slot * 2 * kTileRows;                              // + x * kTileRows
-  const uint32_t bar_slot = 1 + slot;  // named barrier of the slot
-  const bool want_loss = a.loss != nullptr || a.level_loss != nullptr;
-  // the last level's code row is only needed when something other than ids is asked for
-  const bool tail_last = a.emb_out != nullptr || want_loss || a.final_residual != nullptr;
-  // tile identity x (0 = A, 1 = B) -> accumulator columns / completion barriers
-  auto acc_of = [&](int x) -> uint32_t { return tmem_base + (NACC == 2 ? x : slot) * kNTile; };
-  auto unit_bar = [&](int x) -> uint32_t { return ptx::smem_u32(&bar_unit[2 * (NACC == 2 ? x : slot)]); };
-  auto tile_row0 = [&](int k) -> int64_t {  // first row of this slot's tile in the CTA's k-th group
+  const int my_groups = static_cast<int>((n_groups - 1 - blockIdx.x) / gridDim.x + 1);  // grid <= n_groups
+  const int total_tiles = n_levels * n_k;
+  // first row of slot `slot` in this CTA's k-th group (may lie beyond n: the slot then runs on zeros)
+  auto tile_row0 = [&](int k, int slot) -> int64_t {
     return ((static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(k) * gridDim.x) * NSLOT + slot) * kTileRows;
   };
 
-  auto load_image = [&](uint32_t i) {  // image i of this CTA's sequence -> its stage (one thread)
-    const int s = p.resident ? static_cast<int>(i) : static_cast<int>(i % p.stages);
-    const uint32_t bar = ptx::smem_u32(&bar_b_full[s]);
-    ptx::mbar_arrive_expect_tx(bar, p.tile_bytes);
-    ptx::bulk_g2s(ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes),
-                  p.packed + static_cast<size_t>(i % total_tiles) * p.tile_bytes, p.tile_bytes, bar);
-  };
-  if (threadIdx.x == 0) {
-    // resident: every image once; streamed: fill all stages but one (slot 0's issuer adds one image per pair round)
-    const uint32_t first = p.resident ? static_cast<uint32_t>(total_tiles)
-                                      : (n_images < static_cast<uint32_t>(p.stages - 1) ? n_images : p.stages - 1);
-    for (uint32_t i = 0; i < first; ++i) load_image(i);
-  }
+  const int rwarp = warp - kGroupWarps;  // row group = the HIGHER warp ids: the scheduler favours them, and the
+                                         // row work -> MMA issue chain is the critical path of the pipeline
+  if (warp >= kGroupWarps) {
+    // =========================================== row group ====================================================
+    ptx::setmaxnreg_inc<kRowRegs>();
+    const int slot = rwarp / WPS;
+    const int ws = rwarp % WPS;  // warp inside the sub-group
+    const uint32_t n_images = static_cast<uint32_t>(my_groups) * total_tiles;
+    auto load_image = [&](uint32_t i) {  // image i of this CTA's sequence -> its stage (one thread)
+      const int s = p.resident ? static_cast<int>(i) : static_cast<int>(i % p.stages);
+      const uint32_t bar = ptx::smem_u32(&bar_b_full[s]);
+      ptx::mbar_arrive_expect_tx(bar, p.tile_bytes);
+      ptx::bulk_g2s(ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes),
+                    p.packed + static_cast<size_t>(i % total_tiles) * p.tile_bytes, p.tile_bytes, bar);
+    };
+    if (rwarp == 0 && lane == 0) {
+      // resident: every image once; streamed: fill all stages but one (slot 0's issuer adds one image per iteration)
+      const uint32_t first = p.resident ? static_cast<uint32_t>(total_tiles)
+                                        : (n_images < static_cast<uint32_t>(p.stages - 1) ? n_images : p.stages - 1);
+      for (uint32_t i = 0; i < first; ++i) load_image(i);
+    }
+    const int j = lane % L::RPI, kc = lane / L::RPI;
+    const int rc_row0 = ws * (RPT * L::RPI) + j;  // + g * RPI
+    const uint32_t ones = ptx::smem_u32(s_ones);
+    const uint32_t a_hi = ptx::smem_u32(s_a + slot * p.a_bytes);
+    const uint32_t a_lo = a_hi + p.a_bytes / 2;
+    const uint32_t bar_slot = 1 + slot;  // named barrier of the sub-group
+    const uint32_t bar_scan = ptx::smem_u32(&bar_scan_done[slot]);
+    const uint32_t turn_addr = ptx::smem_u32(s_turn);
+    const uint2* cand = reinterpret_cast<const uint2*>(s_cand + slot * kCandSlotBytes);  // [half][row]
+    float* my_loss = s_loss + slot * kTileRows;
+    const bool want_loss = a.loss != nullptr || a.level_loss != nullptr;
+    // the last level's code row is only needed when something other than ids is asked for
+    const bool tail_last = a.emb_out != nullptr || want_loss || a.final_residual != nullptr;
+    uint32_t scan_phase = 0;
 
-  // ---- row-tile helpers (row-cooperative layout) ----
-  auto load_x = [&](float(&r)[RPT][8], int k, int x) {
-    const int64_t row0 = tile_row0(k);
-    if (wt == 0 && lane == 0 && k + 2 < G) {  // pull the tile after this one into L2
-      const int64_t next0 = tile_row0(k + 2);
-      if (next0 < a.n) {
-        const int64_t rows = a.n - next0 < kTileRows ? a.n - next0 : kTileRows;
-        ptx::bulk_prefetch_l2(a.x + next0 * D, static_cast<uint32_t>(rows * D * 4));
+    for (int k = 0; k < my_groups; ++k) {
+      const int64_t row0 = tile_row0(k, slot);
+      if (ws == 0 && lane == 0 && k + 1 < my_groups) {  // pull the slot's next row tile into L2
+        const int64_t next0 = tile_row0(k + 1, slot);
+        if (next0 < a.n) {
+          const int64_t rows = a.n - next0 < kTileRows ? a.n - next0 : kTileRows;
+          ptx::bulk_prefetch_l2(a.x + next0 * D, static_cast<uint32_t>(rows * D * 4));
+        }
       }
-    }
+      float r[RPT][8];
+      if (slot == 0 && ws == 0) stamp(0, 1);
 #pragma unroll
-    for (int g = 0; g < RPT; ++g) {
-      const int row = rc_row0 + g * L::RPI;
-      const int64_t grow = row0 + row;
-      if (grow < a.n) {
-        const float4* src = reinterpret_cast<const float4*>(a.x + grow * D + kc * 8);
-        const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
-        r[g][0] = v0.x, r[g][1] = v0.y, r[g][2] = v0.z, r[g][3] = v0.w;
-        r[g][4] = v1.x, r[g][5] = v1.y, r[g][6] = v1.z, r[g][7] = v1.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r[g][i] = 0.f;
-      }
-      if (want_loss && kc == 0) loss_base[x * kTileRows + row] = 0.f;
-    }
-  };
-  // residual -> A operand (bf16 hi | lo) of tile x, optionally stored as residuals[l]
-  auto stage = [&](const float(&r)[RPT][8], int k, int l, int x) {
-    const int64_t row0 = tile_row0(k);
-    const uint32_t a_hi = a_base + x * p.a_bytes, a_lo = a_hi + p.a_bytes / 2;
-#pragma unroll
-    for (int g = 0; g < RPT; ++g) {
-      const int row = rc_row0 + g * L::RPI;
-      uint4 hi, lo;
-      split8(r[g], hi, lo);
-      sts128(a_hi + kc * (kTileRows * 16) + row * 16, hi);
-      sts128(a_lo + kc * (kTileRows * 16) + row * 16, lo);
-      if (a.residuals != nullptr) {
-        const int64_t grow = row0 + row;
+      for (int g = 0; g < RPT; ++g) {
+        const int64_t grow = row0 + rc_row0 + g * L::RPI;
         if (grow < a.n) {
-          float4* dst = reinterpret_cast<float4*>(a.residuals + (static_cast<int64_t>(l) * a.n + grow) * D + kc * 8);
-          dst[0] = make_float4(r[g][0], r[g][1], r[g][2], r[g][3]);
-          dst[1] = make_float4(r[g][4], r[g][5], r[g][6], r[g][7]);
+          const float4* src = reinterpret_cast<const float4*>(a.x + grow * D + kc * 8);
+          const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+          r[g][0] = v0.x, r[g][1] = v0.y, r[g][2] = v0.z, r[g][3] = v0.w;
+          r[g][4] = v1.x, r[g][5] = v1.y, r[g][6] = v1.z, r[g][7] = v1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) r[g][i] = 0.f;
         }
+        if (want_loss && kc == 0) my_loss[rc_row0 + g * L::RPI] = 0.f;
       }
-    }
-    ptx::fence_proxy_async_smem();
-  };
-  // issue the MMAs of tile x at (group k, level l, image t); called by the slot's warp 0 after a slot barrier
-  // (b_follows: tile B has a group in this pair round and will use the image after tile A)
-  auto issue = [&](int k, int l, int t, int x, bool b_follows) {
-    const uint32_t P = static_cast<uint32_t>((k >> 1) * total_tiles + l * n_k + t);  // pair round = image index
-    const int s = p.resident ? l * n_k + t : static_cast<int>(P % p.stages);
-    ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), p.resident ? 0u : (P / p.stages) & 1u);
-    ptx::tc_fence_after_sync();
-    if (ptx::elect_one()) {
-      const uint32_t a_hi = a_base + x * p.a_bytes;
-      const uint32_t b_tile = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
-      const uint32_t acc_col = acc_of(x);
-      const uint32_t bar0 = unit_bar(x);
-      issue_unit<D>(acc_col, a_hi, a_hi + p.a_bytes / 2, ones, b_tile, 0, bar0);
-      issue_unit<D>(acc_col + kUnitCols, a_hi, a_hi + p.a_bytes / 2, ones, b_tile, kUnitCols, bar0 + 8);
-      // the image is released once both tiles of the slot have used it: the commit after B's (or a lone A's) MMAs
-      if (!p.resident && (x == 1 || !b_follows)) {
-        ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
-        if (slot == 0) {
-          // refill: image P + stages - 1 goes where image P - 1 was, once every slot's MMAs on it are done
-          const uint32_t nxt = P + p.stages - 1;
-          if (nxt < n_images) {
-            if (P > 0) {
-              const uint32_t prev = P - 1;
-              ptx::mbar_wait(ptx::smem_u32(&bar_b_empty[prev % p.stages]), (prev / p.stages) & 1u);
-            }
-            load_image(nxt);
-          }
-        }
-      }
-    }
-    __syncwarp();
-  };
 
-  // ---- state of the two row tiles: c = current, o = other; x = identity of c (0 = A, 1 = B) ----
-  float rc[RPT][8], ro[RPT][8];
-  int k_c = 0, l_c = 0, t_c = 0, k_o = 1, l_o = 0, t_o = 0;
-  float best_c = -INFINITY, best_o = -INFINITY;
-  int bcol_c = 0, bcol_o = 0;
-  uint32_t ph_c = 0, ph_o = 0;  // completion-barrier phases (NACC == 1: ph_c is the slot's single sequence)
-  int x = 0;
-
-  if (k_c < G) {
-    load_x(rc, k_c, 0);
-    stage(rc, k_c, 0, 0);
-  }
-  if (k_o < G) {
-    load_x(ro, k_o, 1);
-    stage(ro, k_o, 0, 1);
-  }
-  ptx::named_bar_sync(bar_slot, kSlotThreads);
-  if (wt == 0 && k_c < G) issue(k_c, 0, 0, 0, k_c + 1 < G);
-
-  while (k_c < G || k_o < G) {
-    if (NACC == 2) {
-      // oth's A operand is staged and its accumulator drained (previous step): queue its MMAs behind cur's
-      ptx::tc_fence_before_sync();
-      ptx::named_bar_sync(bar_slot, kSlotThreads);
-      if (wt == 0 && k_o < G) issue(k_o, l_o, t_o, x ^ 1, k_o + 1 < G);
-    }
-    if (k_c < G) {
-      // ---- scan ----
-      float m;
-      int col;
-      const uint32_t acc_addr = acc_of(x) + (static_cast<uint32_t>(q * 32) << 16);
-      const uint32_t bar0 = unit_bar(x);
-      scan_accumulator(acc_addr, h, bar0, bar0 + 8, ph_c, tile_row0(k_c) + scan_row < a.n, m, col);
-      if (NACC == 2) ph_c ^= 1;
-      if (m > best_c) {  // strict: an earlier image keeps exact ties
-        best_c = m;
-        bcol_c = t_c * kNTile + col;
-      }
-      if (t_c == n_k - 1) {
-        const uint32_t caddr = cand_base + x * kCandSlotBytes + (h * kTileRows + scan_row) * 8;
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(caddr), "r"(__float_as_uint(best_c)), "r"(bcol_c) : "memory");
-      }
-    }
-    if (NACC == 1) {
-      if (k_c < G) ph_c ^= 1;  // one completion per issued tile, in scan order
-      ptx::tc_fence_before_sync();
-      ptx::named_bar_sync(bar_slot, kSlotThreads);
-      if (wt == 0 && k_o < G) issue(k_o, l_o, t_o, x ^ 1, k_o + 1 < G);
-    } else {
-      ptx::named_bar_sync(bar_slot, kSlotThreads);
-    }
-    if (k_c < G) {
-      if (t_c < n_k - 1) {
-        ++t_c;
-      } else {
-        // ---- row work: merge the two halves of every row, write ids, gather, value / loss / next residual ----
-        const int64_t row0 = tile_row0(k_c);
-        const float* cb = a.codebooks + static_cast<int64_t>(l_c) * a.k * D;
-        const bool last = l_c + 1 == n_levels;
-        const bool tail = !last || tail_last;
-        const uint32_t cand = cand_base + x * kCandSlotBytes;
-        float* my_loss = loss_base + x * kTileRows;
-        float e[RPT][8];
+      for (int l = 0; l < n_levels; ++l) {
+        if (slot == 0 && ws == 0) stamp(0, 2);
+        // ---- stage the residual as the A operand (bf16 hi | lo), optionally store it ----
 #pragma unroll
         for (int g = 0; g < RPT; ++g) {
           const int row = rc_row0 + g * L::RPI;
-          uint32_t m0b, c0, m1b, c1;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(m0b), "=r"(c0) : "r"(cand + row * 8) : "memory");
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(m1b), "=r"(c1) : "r"(cand + (kTileRows + row) * 8) : "memory");
-          const float m0 = __uint_as_float(m0b), m1 = __uint_as_float(m1b);
-          const bool first = m0 > m1 || (m0 == m1 && c0 < c1);  // lowest column wins exact ties
-          uint32_t k_sel = first ? c0 : c1;
-          k_sel = k_sel < static_cast<uint32_t>(a.k) ? k_sel : static_cast<uint32_t>(a.k - 1);
-          const int64_t grow = row0 + row;
-          if (kc == 0 && grow < a.n) a.ids[grow * a.ids_row_stride + l_c * a.ids_level_stride] = k_sel;
-          if (tail) {
-            const float4* src = reinterpret_cast<const float4*>(cb + static_cast<int64_t>(k_sel) * D + kc * 8);
-            const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
-            e[g][0] = v0.x, e[g][1] = v0.y, e[g][2] = v0.z, e[g][3] = v0.w;
-            e[g][4] = v1.x, e[g][5] = v1.y, e[g][6] = v1.z, e[g][7] = v1.w;
-          }
-        }
-        if (tail) {
-#pragma unroll
-          for (int g = 0; g < RPT; ++g) {
-            const int row = rc_row0 + g * L::RPI;
+          uint4 hi, lo;
+          split8(r[g], hi, lo);
+          sts128(a_hi + kc * (kTileRows * 16) + row * 16, hi);
+          sts128(a_lo + kc * (kTileRows * 16) + row * 16, lo);
+          if (a.residuals != nullptr) {
             const int64_t grow = row0 + row;
-            const bool valid = grow < a.n;
-            float o[8];
-            float ll = 0.f;
-            if (want_loss) {
-              float sq = 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float df = rc[g][i] - e[g][i];
-                sq = fmaf(df, df, sq);
-              }
-              sq = row_sum<D>(sq);
-              ll = sq + a.beta * sq;  // (modules/loss.py:41-44)
-            }
-            if constexpr (!ROT) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = e[g][i];
-            } else {
-              // modules/quantize.py:34-45,134-140:  o = r - 2 (r.w) w + 2 (r.u) q
-              float rr = 0.f, ee = 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                rr = fmaf(rc[g][i], rc[g][i], rr);
-                ee = fmaf(e[g][i], e[g][i], ee);
-              }
-              rr = row_sum<D>(rr);
-              ee = row_sum<D>(ee);
-              const float inv_r = 1.0f / (sqrtf(rr) + 1e-8f);  // u = r / (|r| + 1e-8)
-              const float inv_e = 1.0f / (sqrtf(ee) + 1e-8f);  // q = e / (|e| + 1e-8)
-              float ss = 0.f, ru = 0.f, rs = 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float u = rc[g][i] * inv_r;
-                const float qv = e[g][i] * inv_e;
-                const float sv = u + qv;
-                ss = fmaf(sv, sv, ss);
-                ru = fmaf(rc[g][i], u, ru);
-                rs = fmaf(rc[g][i], sv, rs);
-              }
-              ss = row_sum<D>(ss);
-              ru = row_sum<D>(ru);
-              rs = row_sum<D>(rs);
-              const float inv_s = 1.0f / fmaxf(sqrtf(ss), 1e-6f);  // w = (u+q) / max(|u+q|, 1e-6)
-              const float rw2 = 2.0f * (rs * inv_s);               // 2 (r.w)
-              const float ru2 = 2.0f * ru;                         // 2 (r.u)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float u = rc[g][i] * inv_r;
-                const float qv = e[g][i] * inv_e;
-                const float w = (u + qv) * inv_s;
-                o[i] = rc[g][i] - rw2 * w + ru2 * qv;
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rc[g][i] = rc[g][i] - o[i];
-            if (valid && a.emb_out != nullptr) {
-              float4* dst = reinterpret_cast<float4*>(a.emb_out + (static_cast<int64_t>(l_c) * a.n + grow) * D + kc * 8);
-              dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-              dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-            }
-            if (want_loss && kc == 0) {
-              const float tot = my_loss[row] + ll;  // private to this thread
-              my_loss[row] = tot;
-              if (valid) {
-                if (a.level_loss != nullptr) a.level_loss[static_cast<int64_t>(l_c) * a.n + grow] = ll;
-                if (last && a.loss != nullptr) a.loss[grow] = tot;
-              }
-            }
-            if (last && valid && a.final_residual != nullptr) {
-              float4* dst = reinterpret_cast<float4*>(a.final_residual + grow * D + kc * 8);
-              dst[0] = make_float4(rc[g][0], rc[g][1], rc[g][2], rc[g][3]);
-              dst[1] = make_float4(rc[g][4], rc[g][5], rc[g][6], rc[g][7]);
+            if (grow < a.n) {
+              float4* dst = reinterpret_cast<float4*>(a.residuals + (static_cast<int64_t>(l) * a.n + grow) * D + kc * 8);
+              dst[0] = make_float4(r[g][0], r[g][1], r[g][2], r[g][3]);
+              dst[1] = make_float4(r[g][4], r[g][5], r[g][6], r[g][7]);
             }
           }
         }
-        t_c = 0;
-        best_c = -INFINITY;
-        bcol_c = 0;
-        if (last) {  // next row tile of this kind (A: even groups, B: odd groups)
-          l_c = 0;
-          k_c += 2;
-          if (k_c < G) load_x(rc, k_c, x);
+        ptx::fence_proxy_async_smem();
+        if (ws == 0) {
+          ptx::named_bar_sync(bar_slot, TPS);
+          if (slot == 0) stamp(0, 3);
+          // ---- issue the level's MMAs, one accumulator per operand image, in round-robin order over the slots ----
+          for (int t = 0; t < n_k; ++t) {
+            const uint32_t it = static_cast<uint32_t>((k * n_levels + l) * n_k + t);  // image index in this CTA's sequence
+            const uint32_t s_issue = it * NSLOT + slot;                               // accumulator sequence number
+            const uint32_t acc = s_issue & 1u;
+            if (NSLOT > 1) ptx::counter_wait(turn_addr, s_issue);
+            ptx::mbar_wait(ptx::smem_u32(&bar_acc_free[acc]), ((s_issue >> 1) & 1u) ^ 1u);
+            const int s = p.resident ? l * n_k + t : static_cast<int>(it % p.stages);
+            ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), p.resident ? 0u : (it / p.stages) & 1u);
+            ptx::tc_fence_after_sync();
+            if (ptx::elect_one()) {
+              const uint32_t b_tile = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
+              const uint32_t acc_col = tmem_base + acc * kNTile;
+              if (kAblate && (p.debug & 4)) {
+                ptx::umma_commit(ptx::smem_u32(&bar_mma_done[2 * acc]));
+                ptx::umma_commit(ptx::smem_u32(&bar_mma_done[2 * acc + 1]));
+              } else {
+              issue_unit<D>(acc_col, a_hi, a_lo, ones, b_tile, 0, ptx::smem_u32(&bar_mma_done[2 * acc]));
+              issue_unit<D>(acc_col + kUnitCols, a_hi, a_lo, ones, b_tile, kUnitCols, ptx::smem_u32(&bar_mma_done[2 * acc + 1]));
+              }
+              if (NSLOT > 1) ptx::counter_add_release(turn_addr, 1);
+              if (slot == 0) stamp(0, 4);
+              if (!p.resident) {
+                ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
+                if (slot == 0) {
+                  // refill: image it + stages - 1 goes where image it - 1 was, once every slot's MMAs on it are done
+                  const uint32_t nxt = it + p.stages - 1;
+                  if (nxt < n_images) {
+                    if (it > 0) {
+                      const uint32_t prev = it - 1;
+                      ptx::mbar_wait(ptx::smem_u32(&bar_b_empty[prev % p.stages]), (prev / p.stages) & 1u);
+                    }
+                    load_image(nxt);
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          }
         } else {
-          ++l_c;
+          ptx::named_bar_arrive(bar_slot, TPS);
         }
-        if (k_c < G) stage(rc, k_c, l_c, x);
+
+        // ---- wait for the scan, merge the two halves of every row, write ids, gather, value / loss / residual ----
+        if (slot == 0 && ws == 0) stamp(0, 5);
+        ptx::mbar_wait(bar_scan, scan_phase);
+        scan_phase ^= 1;
+        if (slot == 0 && ws == 0) stamp(0, 6);
+        const float* cb = a.codebooks + static_cast<int64_t>(l) * a.k * D;
+        const bool last = l + 1 == n_levels;
+        const bool tail = !last || tail_last;
+#pragma unroll
+        for (int g0 = 0; g0 < RPT; g0 += GC) {
+          float e[GC][8];
+#pragma unroll
+          for (int gg = 0; gg < GC; ++gg) {
+            const int row = rc_row0 + (g0 + gg) * L::RPI;
+            const uint2 c0 = cand[row], c1 = cand[kTileRows + row];
+            const float m0 = __uint_as_float(c0.x), m1 = __uint_as_float(c1.x);
+            const bool first = m0 > m1 || (m0 == m1 && c0.y < c1.y);  // lowest column wins exact ties
+            uint32_t k_sel = first ? c0.y : c1.y;
+            k_sel = k_sel < static_cast<uint32_t>(a.k) ? k_sel : static_cast<uint32_t>(a.k - 1);
+            const int64_t grow = row0 + row;
+            if (kc == 0 && grow < a.n) a.ids[grow * a.ids_row_stride + l * a.ids_level_stride] = k_sel;
+            if (kAblate && tail && (p.debug & 2)) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) e[gg][i] = 0.25f * r[g0 + gg][i];
+            } else if (tail) {
+              const float4* src = reinterpret_cast<const float4*>(cb + static_cast<int64_t>(k_sel) * D + kc * 8);
+              const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+              e[gg][0] = v0.x, e[gg][1] = v0.y, e[gg][2] = v0.z, e[gg][3] = v0.w;
+              e[gg][4] = v1.x, e[gg][5] = v1.y, e[gg][6] = v1.z, e[gg][7] = v1.w;
+            }
+          }
+          if (slot == 0 && ws == 0) stamp(0, 7);
+          if (tail) {
+#pragma unroll
+            for (int gg = 0; gg < GC; ++gg) {
+              const int g = g0 + gg;
+              const int row = rc_row0 + g * L::RPI;
+              const int64_t grow = row0 + row;
+              const bool valid = grow < a.n;
+              float o[8];
+              float ll = 0.f;
+              if (want_loss) {
+                float sq = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float df = r[g][i] - e[gg][i];
+                  sq = fmaf(df, df, sq);
+                }
+                sq = row_sum<D>(sq);
+                ll = sq + a.beta * sq;  // (modules/loss.py:41-44)
+              }
+              if constexpr (!ROT) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = e[gg][i];
+              } else {
+                // modules/quantize.py:34-45,134-140:  o = r - 2 (r.w) w + 2 (r.u) q
+                float rr = 0.f, ee = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  rr = fmaf(r[g][i], r[g][i], rr);
+                  ee = fmaf(e[gg][i], e[gg][i], ee);
+                }
+                rr = row_sum<D>(rr);
+                ee = row_sum<D>(ee);
+                const float inv_r = 1.0f / (sqrtf(rr) + 1e-8f);  // u = r / (|r| + 1e-8)
+                const float inv_e = 1.0f / (sqrtf(ee) + 1e-8f);  // q = e / (|e| + 1e-8)
+                float ss = 0.f, ru = 0.f, rs = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float u = r[g][i] * inv_r;
+                  const float qv = e[gg][i] * inv_e;
+                  const float sv = u + qv;
+                  ss = fmaf(sv, sv, ss);
+                  ru = fmaf(r[g][i], u, ru);
+                  rs = fmaf(r[g][i], sv, rs);
+                }
+                ss = row_sum<D>(ss);
+                ru = row_sum<D>(ru);
+                rs = row_sum<D>(rs);
+                const float inv_s = 1.0f / fmaxf(sqrtf(ss), 1e-6f);  // w = (u+q) / max(|u+q|, 1e-6)
+                const float rw2 = 2.0f * (rs * inv_s);               // 2 (r.w)
+                const float ru2 = 2.0f * ru;                         // 2 (r.u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float u = r[g][i] * inv_r;
+                  const float qv = e[gg][i] * inv_e;
+                  const float w = (u + qv) * inv_s;
+                  o[i] = r[g][i] - rw2 * w + ru2 * qv;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[g][i] = r[g][i] - o[i];
+              if (valid && a.emb_out != nullptr) {
+                float4* dst = reinterpret_cast<float4*>(a.emb_out + (static_cast<int64_t>(l) * a.n + grow) * D + kc * 8);
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+              }
+              if (want_loss && kc == 0) {
+                const float tot = my_loss[row] + ll;  // private to this thread
+                my_loss[row] = tot;
+                if (valid) {
+                  if (a.level_loss != nullptr) a.level_loss[static_cast<int64_t>(l) * a.n + grow] = ll;
+                  if (last && a.loss != nullptr) a.loss[grow] = tot;
+                }
+              }
+              if (last && valid && a.final_residual != nullptr) {
+                float4* dst = reinterpret_cast<float4*>(a.final_residual + grow * D + kc * 8);
+                dst[0] = make_float4(r[g][0], r[g][1], r[g][2], r[g][3]);
+                dst[1] = make_float4(r[g][4], r[g][5], r[g][6], r[g][7]);
+              }
+            }
+          }
+        }
       }
     }
-    // ---- swap the roles of the two tiles ----
-#pragma unroll
-    for (int g = 0; g < RPT; ++g) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float tmp = rc[g][i];
-        rc[g][i] = ro[g][i];
-        ro[g][i] = tmp;
+  } else {
+    // =========================================== scan group ===================================================
+    ptx::setmaxnreg_dec<kScanRegs>();
+    const int sw = warp;
+    const int q = sw & 3;   // TMEM lane quarter
+    const int h = sw >> 2;  // which 64 columns of each unit this thread scans
+    const int scan_row = q * 32 + lane;
+    uint32_t s = 0;  // accumulators scanned so far
+    for (int k = 0; k < my_groups; ++k) {
+      for (int lt = 0; lt < total_tiles; ++lt) {
+        const int t = lt % n_k;
+#pragma unroll 1
+        for (int slot = 0; slot < NSLOT; ++slot, ++s) {
+          const uint32_t acc = s & 1u, par = (s >> 1) & 1u;
+          const uint32_t acc_addr = tmem_base + acc * kNTile + (static_cast<uint32_t>(q * 32) << 16);
+          float m;
+          int col;
+          if (sw == 0) stamp(1, 10 + slot);
+          if (kAblate && (p.debug & 1)) {
+            ptx::mbar_wait(ptx::smem_u32(&bar_mma_done[2 * acc]), par);
+            ptx::mbar_wait(ptx::smem_u32(&bar_mma_done[2 * acc + 1]), par);
+            m = 0.f, col = scan_row;
+          } else
+          scan_accumulator(acc_addr, h, ptx::smem_u32(&bar_mma_done[2 * acc]), ptx::smem_u32(&bar_mma_done[2 * acc + 1]), par,
+                           tile_row0(k, slot) + scan_row < a.n, m, col);
+          if (sw == 0) stamp(1, 20 + slot);
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_acc_free[acc]));
+          // running (max, column) over the level's operand images lives in the thread's own candidate entry
+          uint2* c = reinterpret_cast<uint2*>(s_cand + slot * kCandSlotBytes) + h * kTileRows + scan_row;
+          col += t * kNTile;
+          if (t > 0) {
+            const uint2 prev = *c;
+            if (!(m > __uint_as_float(prev.x))) {  // strict: an earlier image keeps exact ties
+              m = __uint_as_float(prev.x);
+              col = static_cast<int>(prev.y);
+            }
+          }
+          *c = make_uint2(__float_as_uint(m), static_cast<uint32_t>(col));
+          if (t == n_k - 1) {
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_scan_done[slot]));
+          }
+        }
       }
     }
-    { const int tk = k_c; k_c = k_o; k_o = tk; }
-    { const int tl = l_c; l_c = l_o; l_o = tl; }
-    { const int tt = t_c; t_c = t_o; t_o = tt; }
-    { const float tb = best_c; best_c = best_o; best_o = tb; }
-    { const int tc = bcol_c; bcol_c = bcol_o; bcol_o = tc; }
-    if (NACC == 2) { const uint32_t tp = ph_c; ph_c = ph_o; ph_o = tp; }
-    x ^= 1;
   }
 
+  if (ts_on && (warp == 0 || warp == kGroupWarps)) { const int who = warp == 0 ? 1 : 0; s_ts[who * 384 + 380] = ts_n; }
   ptx::tc_fence_before_sync();
   __syncthreads();
+#ifdef HV_TC_INSTRUMENT
+  if ((p.debug & 64) && blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int who = 0; who < 2; ++who) {
+      const int n = s_ts[who * 384 + 380];
+      for (int i = 0; i < n; ++i) printf("TS %d %u %u\n", who, s_ts[who * 384 + 2 * i], s_ts[who * 384 + 2 * i + 1]);
+    }
+  }
+#endif
   if (warp == 0) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
@@ -728,19 +743,30 @@ int pack_d(const float* codebooks, int n_levels, int k, const TcPlan& plan, uint
   return HV_OK;
 }
 
-template <int D, int NSLOT, int NACC>
+template <int D, int NSLOT>
 int launch_slots(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, const DeviceProps& props, cudaStream_t stream) {
   const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
   const int64_t n_groups = (n_row_tiles + NSLOT - 1) / NSLOT;
   const unsigned grid = static_cast<unsigned>(n_groups < props.sm_count ? n_groups : props.sm_count);
-  TcParams p{packed, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes};
+  static const int debug = [] {
+    const char* e = getenv("HIDVAE_TC_DEBUG");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  TcParams p{packed, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes, debug};
   auto go = [&](auto kernel) -> int {
+    cudaFuncAttributes attr;
+    HV_CUDA_CHECK(cudaFuncGetAttributes(&attr, kernel));
+    if (attr.numRegs * 2 < kRowRegs + kScanRegs) {  // setmaxnreg.inc would wait forever: refuse loudly instead
+      set_error("hv_rq_forward: tcgen05 kernel was built with %d registers/thread, the register hand-over needs %d",
+                attr.numRegs, (kRowRegs + kScanRegs) / 2);
+      return HV_ERR_UNSUPPORTED;
+    }
     HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
-    kernel<<<grid, NSLOT * kSlotThreads, plan.smem_bytes, stream>>>(a, p);
+    kernel<<<grid, kThreads, plan.smem_bytes, stream>>>(a, p);
     HV_CUDA_CHECK(cudaGetLastError());
     return HV_OK;
   };
-  return rot ? go(rq_fwd_tc_kernel<D, true, NSLOT, NACC>) : go(rq_fwd_tc_kernel<D, false, NSLOT, NACC>);
+  return rot ? go(rq_fwd_tc_kernel<D, true, NSLOT>) : go(rq_fwd_tc_kernel<D, false, NSLOT>);
 }
 
 template <int D>
@@ -749,19 +775,24 @@ int launch_d(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, 
     if (int st = pack_d<D>(a.codebooks, a.n_levels, a.k, plan, packed, stream)) return st;
   DeviceProps props;
   if (int st = device_props(&props)) return st;
-  if constexpr (Cfg<D>::NT == 2) {
-    // one slot per CTA while one row tile per SM covers the rows (more SMs at work), else two
-    const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
-    static const int forced = [] {
-      const char* e = getenv("HIDVAE_TC_SLOTS");
-      return e != nullptr ? atoi(e) : 0;
-    }();
-    const bool one = forced == 1 || (forced != 2 && n_row_tiles <= props.sm_count);  // HIDVAE_TC_SLOTS: tuning only
-    return one ? launch_slots<D, 1, 1>(a, rot, plan, packed, props, stream)
-               : launch_slots<D, 2, 1>(a, rot, plan, packed, props, stream);
-  } else {
-    return launch_slots<D, 1, 2>(a, rot, plan, packed, props, stream);
-  }
+  const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
+  // as many row tiles in flight per CTA as it takes to cover them with one CTA per SM (1, 2 or Cfg<D>::NT)
+  const int64_t per_sm = (n_row_tiles + props.sm_count - 1) / props.sm_count;
+  static const int forced = [] {
+    const char* e = getenv("HIDVAE_TC_SLOTS");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  int nslot = per_sm <= 1 ? 1 : (per_sm == 2 ? 2 : Cfg<D>::NT);
+  if (forced == 1 || forced == 2 || (forced == 4 && Cfg<D>::NT == 4)) nslot = forced;  // tuning experiments only
+  if constexpr (Cfg<D>::NT == 4)
+    if (nslot == 4) return launch_slots<D, 4>(a, rot, plan, packed, props, stream);
+  return nslot == 1 ? launch_slots<D, 1>(a, rot, plan, packed, props, stream)
+                    : launch_slots<D, 2>(a, rot, plan, packed, props, stream);
+}
+
+bool use_v7_only() {
+  static const bool on = getenv("HIDVAE_TC_NEW_ONLY") != nullptr;
+  return on;
 }
 
 bool use_v4() {
@@ -828,7 +859,12 @@ int launch_rq_fwd_tc(const RqFwdArgs& a, int d, bool rot, void* workspace, size_
   }
   if (a.n == 0) return HV_OK;
   uint8_t* packed = static_cast<uint8_t*>(workspace);
-  if (use_v4()) {
+  // Measured (profiles/README.md): the previous generation's lock-step warpgroups are still faster for D = 64
+  // (streamed operand images, MMA-bound) and for large training forwards, whose heavier row work (rotation value,
+  // emb_out / loss stores) is spread over 16 warps there instead of this kernel's 8 row warps.
+  const bool outputs = a.emb_out != nullptr || a.loss != nullptr || a.level_loss != nullptr || a.residuals != nullptr;
+  const bool big = a.n > static_cast<int64_t>(kTileRows) * 148;
+  if (use_v4() || ((d == 64 || (outputs && big)) && !use_v7_only())) {
     if (!prepacked)
       if (int st = launch_rq_pack(a.codebooks, a.n_levels, a.k, d, workspace, workspace_bytes, stream)) return st;
     return launch_rq_fwd_tc_v4(a, d, rot, workspace, stream);

@@ -40,7 +40,7 @@ SIGNATURES = {
                               c_int, c_void_p, c_size_t, c_void_p]),
     "hv_rq_backward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
-                               c_void_p, c_void_p, c_void_p, c_void_p]),
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hv_kmeans_accumulate": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
     "hv_kmeans_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -17,7 +17,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import (HV_ALGO_AUTO, HV_ALGO_SIMT, HV_ALGO_SIMT_DIFF, HV_ALGO_TCGEN05, HV_ALGO_TCGEN05_PREPACKED,
-                   HV_MODE_ROTATION_TRICK, HV_MODE_STE, HV_OP_RQ_FORWARD, check, lib)
+                   HV_MODE_ROTATION_TRICK, HV_MODE_STE, HV_OP_RQ_BACKWARD, HV_OP_RQ_FORWARD, check, lib)
 
 ALGOS = {"auto": HV_ALGO_AUTO, "tcgen05": HV_ALGO_TCGEN05, "simt": HV_ALGO_SIMT, "simt_diff": HV_ALGO_SIMT_DIFF,
          "tcgen05_prepacked": HV_ALGO_TCGEN05_PREPACKED}
@@ -141,11 +141,13 @@ def rq_backward(x: Tensor, codebooks: Tensor, ids: Tensor, mode: int, training: 
         gl_stride = g_loss.stride(0) if g_loss.dim() else 0
     if g_level_loss is not None:
         g_level_loss = _f32c(g_level_loss)
+    ws_bytes = int(lib.hv_workspace_bytes(HV_OP_RQ_BACKWARD, n, d, k, n_levels))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     with torch.cuda.device(x.device):
         check(lib.hv_rq_backward(x.data_ptr(), n, d, codebooks.data_ptr(), n_levels, k, int(mode), int(bool(training)),
                                  float(beta), ids.data_ptr(), ids.stride(0), ids.stride(1), _ptr(g_emb), ls, rs,
                                  _ptr(g_loss), gl_stride, _ptr(g_level_loss), g_x.data_ptr(), g_cb.data_ptr(),
-                                 _stream(x)))
+                                 _ptr(ws), ws_bytes, _stream(x)))
     return g_x, g_cb
 
 

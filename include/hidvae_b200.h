@@ -63,7 +63,9 @@ const char* hv_last_error(void);
 /* number of SMs / compute capability of the current device; returns HV_ERR_CUDA when there is none */
 int hv_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
-/* bytes of scratch the op needs for this shape (packed bf16 codebook images for the tcgen05 path). */
+/* bytes of scratch the op can use for this shape: HV_OP_RQ_FORWARD -- the packed bf16 codebook images of the tcgen05
+ * path (independent of n); HV_OP_RQ_BACKWARD -- replicas of the [L, K, D] codebook gradient that spread the
+ * scatter-add over more L2 lines (0 for small n: the op then adds straight into g_codebooks). */
 size_t hv_workspace_bytes(int op, int64_t n, int d, int k, int n_levels);
 
 /*
@@ -110,12 +112,15 @@ int hv_rq_pack_codebooks(const float* codebooks, int n_levels, int k, int d, voi
  *   g_x      [N, D] written
  *   g_codebooks [L, K, D] ACCUMULATED into (caller zeroes); rows are scatter-added by id
  *               (the embedding_dense_backward of quantize.py:97-98)
+ *   workspace   optional scratch of hv_workspace_bytes(HV_OP_RQ_BACKWARD, ...) bytes (contents irrelevant, the op
+ *               zeroes what it uses); NULL or too small = no replicas, same results up to summation order
  */
 int hv_rq_backward(const float* x, int64_t n, int d, const float* codebooks, int n_levels, int k, int mode,
                    int training, float beta, const int64_t* ids, int64_t ids_row_stride,
                    int64_t ids_level_stride, const float* g_emb, int64_t g_emb_level_stride,
                    int64_t g_emb_row_stride, const float* g_loss, int64_t g_loss_stride,
-                   const float* g_level_loss, float* g_x, float* g_codebooks, void* stream);
+                   const float* g_level_loss, float* g_x, float* g_codebooks, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /*
  * K-means codebook init (init/kmeans.py:43-61).  Assignment = hv_rq_forward with n_levels = 1 (ids only).

@@ -45,7 +45,7 @@ def test_version_and_error_channel(lib_mod):
                                    None, None, None, None, 0, None, 0, None)
     assert st == lib_mod.HV_ERR_UNSUPPORTED and "GUMBEL" in lib_mod.last_error()
     st = lib_mod.lib.hv_rq_backward(None, 8, 32, None, 9, 256, 2, 1, 0.25, None, 0, 0, None, 0, 0, None, 0, None, None,
-                                    None, None)
+                                    None, None, 0, None)
     assert st == lib_mod.HV_ERR_UNSUPPORTED
     assert lib_mod.lib.hv_rq_forward(None, 0, 32, None, 3, 256, 2, 0, 0.25, None, 0, 0, None, None, None, None, None, 0,
                                      None, 0, None) == lib_mod.HV_OK  # empty batch is a no-op

@@ -19,6 +19,7 @@ ap.add_argument("--rows", type=int, default=1 << 22)
 ap.add_argument("--shape", default="32,256,3")
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--tag", default="")
+ap.add_argument("--encode-only", action="store_true")
 args = ap.parse_args()
 d, k, L = (int(v) for v in args.shape.split(","))
 torch.cuda.set_device(0)
@@ -28,7 +29,7 @@ packed = ops.pack_codebooks(cbs)
 res = dict(tag=args.tag, impl=os.environ.get("HIDVAE_TC_IMPL", "v5"), rows=args.rows, d=d, k=k, L=L)
 t = bench.time_region(lambda: ops.rq_encode(x, cbs, packed=packed), args.reps, 3, flush) / args.reps
 res.update(encode_ms=t, encode_gitems=args.rows / t / 1e6, encode_tflops=2.0 * k * d * L * args.rows / t / 1e9)
-if d <= 32:
+if d <= 32 and not args.encode_only:
     out = ops.rq_forward(x, cbs, 3, True, 0.4, want_emb=True, want_loss=True, packed=packed)
     tf = bench.time_region(lambda: ops.rq_forward(x, cbs, 3, True, 0.4, want_emb=True, want_loss=True, packed=packed), args.reps, 3, flush) / args.reps
     tb = bench.time_region(lambda: ops.rq_backward(x, cbs, out.ids, 3, True, 0.4, g_emb, g_loss, None), args.reps, 3, flush) / args.reps
