@@ -51,6 +51,16 @@ def peaks():
     return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="B200_PROFILING.md fallback")
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the three C2 kernels, taken from the committed
+    `ncu --set full` capture of this same step (profiles/r01_traffic.json); {} when the file is missing."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f).get("c2_bytes_per_launch", {})
+    return {}
+
+
 def synth(n, d, k, n_levels, seed, device="cpu"):
     """unit-norm encoder outputs, uniform(0,1) codebooks with level 0 row-normalised and the
     later levels centred/scaled to the residual magnitude ("trained-like"), random upstream gradients."""
@@ -265,7 +275,17 @@ def run_native(args):
 
     if world > 1:
         dist.barrier()
-    e2e_ms = time_region(e2e_step, args.steps, args.warmup, flush)
+    # the public API is graph-capturable (no host-side data-dependent branches, every call on the current stream):
+    # a training loop with static shapes replays ONE graph per step -- pinned-host H2D, kernels, D2H included
+    e2e_run, e2e_graphed = e2e_step, False
+    if not args.no_graph:
+        try:
+            e2e_run, e2e_graphed = GraphedStep(e2e_step), True
+        except Exception as e:
+            print(f"[bench] e2e CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager calls", file=sys.stderr)
+            torch.cuda.synchronize()
+    e2e_ms = time_region(e2e_run, args.steps, args.warmup, flush)
+    e2e_eager_ms = time_region(e2e_step, min(args.steps, 100), 3, flush) / min(args.steps, 100) if e2e_graphed else None
     te = torch.tensor([e2e_ms], device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -293,11 +313,14 @@ def run_native(args):
         dict(kernel="rq_fwd_tc_kernel<32> (eval encode)", ms=t_enc, bound="tensor", achieved=flops / (t_enc * 1e-3) / 1e12,
              peak=pk["tensor"], unit="TFLOP/s", hbm_gbs=b_enc / (t_enc * 1e-3) / 1e9),
     ]
-    for kk in kernels:
+    traffic = ncu_traffic()
+    for kk, key in zip(kernels, ("train_forward", "backward", "eval_encode")):
         kk["frac"] = kk["achieved"] / kk["peak"]
+        kk["traffic"] = traffic.get(key)
     dom = max(kernels, key=lambda kk: kk["ms"])
     roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
-                    traffic=None, kernel=dom["kernel"], kernel_ms=dom["ms"], peak_source=pk["source"] + ", burst",
+                    traffic=dom.get("traffic"), traffic_source="profiles/r01_traffic.json (ncu --set full, dram read + write per launch)",
+                    kernel=dom["kernel"], kernel_ms=dom["ms"], peak_source=pk["source"] + ", burst",
                     kernels=kernels)
 
     sweep = None
@@ -314,7 +337,7 @@ def run_native(args):
                     config=dict(WORKLOAD, parallelism=f"dp{world}", items_per_step_per_gpu=n, cuda_graph=graphed,
                                 eager_ms_per_step=eager_ms),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             ms_per_step=e2e_ms / args.steps),
+                             ms_per_step=e2e_ms / args.steps, cuda_graph=e2e_graphed, eager_ms_per_step=e2e_eager_ms),
                     gpu_launches=NativeStep.LAUNCHES_PER_STEP * args.steps, roofline=roofline, cpu_baseline=cpu,
                     clocks=clocks, impl="native")
         if sweep is not None:

@@ -10,6 +10,6 @@ timeout 300 python bench.py --impl reference --steps 50 --warmup 3 > gpurun_out/
 timeout 300 python tools/profile_step.py > gpurun_out/prof_plain.log 2>&1 && \
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_list.log 2>&1
 echo "ncu_list rc=$?" >> gpurun_out/status.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:rq_fwd_tc|rq_bwd" -c 12 -o gpurun_out/prof_tc -f python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:rq_fwd_tc|rq_bwd" -c 14 -o gpurun_out/prof_tc -f python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1
 echo "ncu_full rc=$?" >> gpurun_out/status.txt
 cat gpurun_out/status.txt; tail -5 gpurun_out/pytest_all.log; cat gpurun_out/bench.json | head -c 3000
