@@ -117,9 +117,11 @@ def rq_forward(x: Tensor, codebooks: Tensor, mode: int = HV_MODE_STE, training: 
 
 
 def rq_backward(x: Tensor, codebooks: Tensor, ids: Tensor, mode: int, training: bool, beta: float,
-                g_emb: Optional[Tensor], g_loss: Optional[Tensor], g_level_loss: Optional[Tensor]):
+                g_emb: Optional[Tensor], g_loss: Optional[Tensor], g_level_loss: Optional[Tensor],
+                use_workspace: bool = True):
     """hv_rq_backward.  g_emb is indexed [L, N, D] (any strides with unit stride in D), g_loss [N] (any stride),
-    g_level_loss [L, N].  Returns (g_x [N, D], g_codebooks [L, K, D])."""
+    g_level_loss [L, N].  Returns (g_x [N, D], g_codebooks [L, K, D]).  `use_workspace=False` withholds the
+    gradient-replica scratch (large N then scatter-adds straight into g_codebooks; same result up to summation order)."""
     _require_cuda(x, codebooks, ids)
     x = _f32c(x)
     codebooks = _f32c(codebooks)
@@ -141,7 +143,7 @@ def rq_backward(x: Tensor, codebooks: Tensor, ids: Tensor, mode: int, training: 
         gl_stride = g_loss.stride(0) if g_loss.dim() else 0
     if g_level_loss is not None:
         g_level_loss = _f32c(g_level_loss)
-    ws_bytes = int(lib.hv_workspace_bytes(HV_OP_RQ_BACKWARD, n, d, k, n_levels))
+    ws_bytes = int(lib.hv_workspace_bytes(HV_OP_RQ_BACKWARD, n, d, k, n_levels)) if use_workspace else 0
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     with torch.cuda.device(x.device):
         check(lib.hv_rq_backward(x.data_ptr(), n, d, codebooks.data_ptr(), n_levels, k, int(mode), int(bool(training)),

@@ -163,6 +163,60 @@ def test_exact_ties_take_first_index(ops):
         assert (ids == 7).all(), algo
 
 
+def test_exact_ties_across_chunks_units_and_halves(ops):
+    """The tensor-core scan folds a row's 256 scores into column classes and chunk maxima; a second maximiser in the
+    same class (other chunk), the other 128-code unit, the other column half or the next operand image must all send
+    the row down the exact first-index path."""
+    d, k = 32, 512
+    gen = torch.Generator().manual_seed(5)
+    for first, dups in [(5, [37]), (5, [133]), (5, [69]), (5, [5 + 256]), (100, [101, 228, 300]), (200, [201]), (31, [32, 63, 64])]:
+        cb = make_codebooks(1, k, d, seed=6)
+        for j in dups:
+            cb[0, j] = cb[0, first]
+        x = cb[0, first].repeat(300, 1) + 1e-3 * torch.randn(300, d, generator=gen)
+        for algo in ALGOS:
+            ids = ops.rq_encode(_dev(x), _dev(cb), algo=algo).cpu().view(-1)
+            assert (ids == first).all(), (algo, first, dups, ids.unique())
+
+
+def test_zero_rows_and_mixed_batch(ops):
+    """All-zero rows score -|c|^2/2 for every code (massive near-ties at a normalised level 0): the kernel must
+    stay finite, pick a code of minimal norm, and leave the other rows of the same warp untouched."""
+    n, d, k, L = 300, 32, 256, 3
+    x = unit_rows(n, d, seed=41)
+    x[::7] = 0.0
+    cbs = make_codebooks(L, k, d, seed=42)
+    out = ops.rq_forward(_dev(x), _dev(cbs), O.MODE_STE, False, 0.25, want_emb=True, want_loss=True, algo="tcgen05")
+    ids = out.ids.cpu()
+    nz = x.abs().sum(1) > 0
+    check_ids(ids[nz], x[nz], cbs, O.MODE_STE, 0.25, False)
+    assert torch.isfinite(out.loss).all() and torch.isfinite(out.emb_out).all()
+    # zero rows: the chosen level-0 code has (near-)minimal norm among the codes
+    nrm = (cbs[0] ** 2).sum(1)
+    assert (nrm[ids[~nz, 0]] <= nrm.min() * (1 + 1e-5)).all()
+
+
+def test_backward_gradient_replicas(ops):
+    """Large N: the codebook gradient is scatter-added into replicas (workspace) and folded; same numbers as the
+    direct scatter-add up to fp32 summation order, g_x bit-identical."""
+    n, d, k, L = 40000, 32, 256, 3
+    assert ops.lib.hv_workspace_bytes(1, n, d, k, L) > 0 and ops.lib.hv_workspace_bytes(1, 1024, d, k, L) == 0  # op 1 = backward
+    x, cbs = _dev(unit_rows(n, d, 51)), _dev(make_codebooks(L, k, d, 52))
+    gen = torch.Generator().manual_seed(53)
+    g_emb, g_loss = _dev(torch.randn(L, n, d, generator=gen)), _dev(torch.randn(n, generator=gen))
+    ids = ops.rq_encode(x, cbs)
+    gx_a, gc_a = ops.rq_backward(x, cbs, ids, O.MODE_ROTATION_TRICK, True, 0.4, g_emb, g_loss, None)
+    gx_b, gc_b = ops.rq_backward(x, cbs, ids, O.MODE_ROTATION_TRICK, True, 0.4, g_emb, g_loss, None, use_workspace=False)
+    assert torch.equal(gx_a, gx_b)
+    # ~150 randomly signed O(1) terms per code: fp32 sums in two different orders differ by ~1e-4 absolute
+    torch.testing.assert_close(gc_a, gc_b, rtol=1e-3, atol=3e-4)
+    # and against a dense fp64 scatter-add of the per-row terms 2 (e - r_l) g_loss of the level-0 codebook
+    e0 = cbs[0][ids[:, 0]].double()
+    ref0 = torch.zeros(k, d, dtype=torch.float64, device="cuda").index_add_(0, ids[:, 0], 2.0 * (e0 - x.double()) * g_loss.double()[:, None])
+    torch.testing.assert_close(gc_a[0].double(), ref0, rtol=1e-3, atol=3e-4)
+    torch.testing.assert_close(gc_b[0].double(), ref0, rtol=1e-3, atol=3e-4)
+
+
 @pytest.mark.parametrize("algo", ALGOS)
 def test_ids_out_strided(ops, algo):
     """ids may be written into a caller-provided [N, L] view (e.g. a column block of the [N, L + L_tags] table the
