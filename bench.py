@@ -212,7 +212,9 @@ def run_native(args):
     assert torch.cuda.is_available(), "bench.py (native arm) needs a CUDA device; there is no CPU fallback"
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a stuck collective must abort the run, not hang it (the watchdog raises after 3 minutes)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     from hidvae_b200 import ops
 
     w = WORKLOAD
@@ -342,10 +344,16 @@ def run_native(args):
                     clocks=clocks, impl="native")
         if sweep is not None:
             line["sweep"] = sweep
-        print(json.dumps(line))
+        OUT.emit(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # No collective is pending (every rank passed the last all-reduce before rank 0 started its CPU baseline).
+        # The captured graphs still hold NCCL kernels, and tearing the communicator down under them was seen to hang
+        # (2 x B200, NCCL 2.28.9): drop the graphs, drain the device and leave without the NCCL teardown.
+        del run_step, e2e_run
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_sweep(ops, pk, flush):
@@ -430,14 +438,39 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = n * steps / dt
     sample = f"{steps} full steps of the 12,101-item workload (oracle/rq.py, torch {torch.__version__} CPU, {cores} threads)"
-    print(json.dumps(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 5),
+    OUT.emit(json.dumps(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 5),
                           ms_per_step=dt / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                           dtype="f32", data="synthetic", config=dict(WORKLOAD, parallelism="cpu"), impl="reference",
                           cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
                           e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
 
+class QuietStdout:
+    """Everything but the final JSON line goes to stderr: libraries print to fd 1 on their own (NCCL's version banner),
+    and the contract is ONE line on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+OUT = None
+
+
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
@@ -447,10 +480,11 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_native(args)
+    with QuietStdout() as OUT:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_native(args)
 
 
 if __name__ == "__main__":
