@@ -13,6 +13,8 @@
 // small N) with global red.add.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace hv {
@@ -20,6 +22,9 @@ namespace {
 
 constexpr int kMaxLevels = 8;
 constexpr int kBwdThreads = 256;
+#ifndef HV_BWD_MINB
+#define HV_BWD_MINB 3  // CTAs per SM the exact-level instantiations are compiled for (register cap 80)
+#endif
 
 struct RqBwdArgs {
   const float* x;
@@ -61,10 +66,13 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 
-// LMAX bounds the per-row register arrays (residual and code of every level): 4 covers every shipped config and
-// keeps the kernel at 3+ CTAs per SM; 8 is the general instantiation.
-template <int D, bool ROT, bool SMEM_ACC, int LMAX>
-__global__ void __launch_bounds__(kBwdThreads, LMAX <= 4 ? 3 : 1) rq_bwd_kernel(RqBwdArgs a) {
+// NL > 0: exactly NL levels, known at compile time (no per-level branches, register arrays of that size; 1..4 cover
+// every shipped config and keep the kernel at 3+ CTAs per SM); NL == 0: runtime level count up to kMaxLevels.
+// ROT / TRAIN: rotation-trick Jacobian / training semantics (eval: emb_out = e for every mode, quantize.py:146-147).
+template <int D, bool ROT, bool TRAIN, int NL>
+__global__ void __launch_bounds__(kBwdThreads, NL > 0 ? HV_BWD_MINB : 1) rq_bwd_kernel(RqBwdArgs a) {
+  constexpr int LMAX = NL > 0 ? NL : kMaxLevels;
+  constexpr bool SMEM_ACC = false;  // shared-memory accumulation measured ATOMS-bound (profiles/README.md); kept for experiments
   constexpr int LPR = D / 4;  // lanes per row
   constexpr int ROWS_PER_WARP = 32 / LPR;
   extern __shared__ __align__(16) float s_gc[];  // [L, K, D] when SMEM_ACC
@@ -80,7 +88,7 @@ __global__ void __launch_bounds__(kBwdThreads, LMAX <= 4 ? 3 : 1) rq_bwd_kernel(
   const int warp_global = (blockIdx.x * kBwdThreads + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * kBwdThreads) >> 5;
   const int64_t n_groups = (a.n + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
-  const bool rot = ROT && a.training;
+  constexpr bool rot = ROT && TRAIN;
   float* gc_base = a.n_replicas > 0 ? a.replicas + static_cast<int64_t>(blockIdx.x % a.n_replicas) * lkd : a.g_codebooks;
 
   for (int64_t g = warp_global; g < n_groups; g += n_warps) {
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(kBwdThreads, LMAX <= 4 ? 3 : 1) rq_bwd_kernel(
     float4 r = __ldg(reinterpret_cast<const float4*>(a.x + rrow * D) + sub);
 #pragma unroll
     for (int l = 0; l < LMAX; ++l) {
-      if (l < a.n_levels) {
+      if (NL > 0 || l < a.n_levels) {
         int64_t code = a.ids[rrow * a.ids_row_stride + l * a.ids_level_stride];
         code = code < 0 ? 0 : (code >= a.k ? a.k - 1 : code);
         id[l] = static_cast<int>(code);
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(kBwdThreads, LMAX <= 4 ? 3 : 1) rq_bwd_kernel(
     for (int l = 0; l < LMAX; ++l) {
       GE[l] = make_float4(0.f, 0.f, 0.f, 0.f);
       GL[l] = gl_all;
-      if (l < a.n_levels) {
+      if (NL > 0 || l < a.n_levels) {
         if (a.g_emb != nullptr)
           GE[l] = __ldg(reinterpret_cast<const float4*>(a.g_emb + l * a.g_emb_level_stride + rrow * a.g_emb_row_stride) + sub);
         if (a.g_level_loss != nullptr) GL[l] += a.g_level_loss[static_cast<int64_t>(l) * a.n + rrow];
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(kBwdThreads, LMAX <= 4 ? 3 : 1) rq_bwd_kernel(
     float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int l = LMAX - 1; l >= 0; --l) {
-      if (l < a.n_levels) {
+      if (NL > 0 || l < a.n_levels) {
         const float gl = GL[l];
         const float4 ge = GE[l];
         float4 h = make_float4(ge.x - G.x, ge.y - G.y, ge.z - G.z, ge.w - G.w);
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(kBwdThreads, LMAX <= 4 ? 3 : 1) rq_bwd_kernel(
         const float c2 = 2.0f * gl;
         float4 ge_code = make_float4(-c2 * diff.x, -c2 * diff.y, -c2 * diff.z, -c2 * diff.w);
         const float cb2 = a.beta * c2;
-        if (a.training) {
+        if (TRAIN) {
           float4 jh = h;
           if (rot) {
             const float ir = inv_r[l], ie = inv_e[l], is = inv_s[l];
@@ -205,25 +213,36 @@ int launch_d(const RqBwdArgs& a, bool rot, cudaStream_t stream) {
   if (int st = device_props(&props)) return st;
   constexpr int LPR = D / 4;
   constexpr int rows_per_cta = (kBwdThreads / 32) * (32 / LPR);
-  const size_t acc_bytes = static_cast<size_t>(a.n_levels) * a.k * D * sizeof(float);
-  // shared-memory accumulation pays off once every CTA sees clearly more rows than it has accumulators to flush
-  // Shared-memory accumulation measured ATOMS-bound (555 GB/s at 1M rows, D=32 K=256 L=3): one red.v4 per lane to
-  // the L2-resident [L, K, D] gradient is the default; the shared variant stays selectable for experiments.
-  const bool smem_acc = false && acc_bytes <= 100 * 1024 && a.n >= static_cast<int64_t>(props.sm_count) * a.k * 4;
   int64_t ctas = (a.n + rows_per_cta - 1) / rows_per_cta;
-  const int64_t cap = static_cast<int64_t>(props.sm_count) * (smem_acc ? 2 : 16);
+  const int64_t cap = static_cast<int64_t>(props.sm_count) * 16;
   if (ctas > cap) ctas = cap;
-  auto go = [&](auto kernel, size_t smem) -> int {
-    if (smem > 48 * 1024) HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<static_cast<unsigned>(ctas), kBwdThreads, smem, stream>>>(a);
+  auto go = [&](auto kernel) -> int {
+    kernel<<<static_cast<unsigned>(ctas), kBwdThreads, 0, stream>>>(a);
     HV_CUDA_CHECK(cudaGetLastError());
     return HV_OK;
   };
-  if (smem_acc) return rot ? go(rq_bwd_kernel<D, true, true, kMaxLevels>, acc_bytes) : go(rq_bwd_kernel<D, false, true, kMaxLevels>, acc_bytes);
-  if (a.n_levels <= 4) return rot ? go(rq_bwd_kernel<D, true, false, 4>, 0) : go(rq_bwd_kernel<D, false, false, 4>, 0);
-  return rot ? go(rq_bwd_kernel<D, true, false, kMaxLevels>, 0) : go(rq_bwd_kernel<D, false, false, kMaxLevels>, 0);
+  const bool train = a.training != 0;
+  const bool r = rot && train;  // eval: the rotation plays no part
+  auto pick = [&](auto nl) -> int {
+    constexpr int NLc = decltype(nl)::value;
+    if (r) return go(rq_bwd_kernel<D, true, true, NLc>);
+    return train ? go(rq_bwd_kernel<D, false, true, NLc>) : go(rq_bwd_kernel<D, false, false, NLc>);
+  };
+  if constexpr (D == 16 || D == 32 || D == 64) {  // the shipped shapes get exact-level instantiations
+    switch (a.n_levels) {
+      case 1: return pick(std::integral_constant<int, 1>{});
+      case 2: return pick(std::integral_constant<int, 2>{});
+      case 3: return pick(std::integral_constant<int, 3>{});
+      case 4: return pick(std::integral_constant<int, 4>{});
+      default: break;
+    }
+  }
+  return pick(std::integral_constant<int, 0>{});
 }
 
+}  // namespace
+
+namespace {
 // g_codebooks += sum over the replicas (they were zeroed before the main kernel ran)
 __global__ void rq_bwd_fold_replicas_kernel(const float* __restrict__ replicas, int n_replicas, int64_t lkd4,
                                             float* __restrict__ g_codebooks) {
