@@ -9,6 +9,7 @@ beta=0.4, ROTATION_TRICK (configs/h_rqvae_amazon.gin).  ONE STEP = one pass of t
     (1) training forward   hv_rq_forward (ids, emb_out, loss)           modules/quantize.py:100-154 x 3 levels
     (2) fused backward     hv_rq_backward (g_x, g_codebooks)            autograd of the same
     (3) eval encode        hv_rq_forward (ids only)                     modules/tokenizer/h_semids.py:127-130
+        (independent of (1)-(2) once the operand image is packed: it runs on a side stream beside them)
 `value` = items / second with inputs resident in HBM (C-ABI calls, CUDA events, L2 flushed between steps);
 `e2e`   = the same pass through the public autograd API from PINNED HOST buffers: H2D of the step's inputs, the
           three kernels, D2H of ids + loss inside the timed region.
@@ -126,6 +127,8 @@ class NativeStep:
 
     def __init__(self, ops, x, cbs, g_emb, g_loss, beta):
         self.ops, self.x, self.cbs, self.g_emb, self.g_loss, self.beta = ops, x, cbs, g_emb, g_loss, beta
+        self.side = torch.cuda.Stream()   # the eval encode depends only on x and the packed image: it runs beside
+                                          # the training forward / backward (a fork/join the CUDA graph keeps)
 
     def train_fwd(self, packed):
         return self.ops.rq_forward(self.x, self.cbs, MODE_ROT, True, self.beta, want_emb=True, want_loss=True, packed=packed)
@@ -137,14 +140,18 @@ class NativeStep:
         return self.ops.rq_encode(self.x, self.cbs, packed=packed)
 
     def __call__(self, comm=None):
+        main = torch.cuda.current_stream()
         packed = self.ops.pack_codebooks(self.cbs)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            ids = self.encode(packed)
         out = self.train_fwd(packed)
         g_x, g_cb = self.bwd(out.ids)
         if comm is not None:
             comm.allreduce_async(g_cb)
-        ids = self.encode(packed)
-        if comm is not None:
             comm.wait()
+        main.wait_stream(self.side)
+        packed.record_stream(self.side)
         return out, g_x, g_cb, ids
 
 
@@ -258,22 +265,30 @@ def run_native(args):
     loss_h = torch.empty((), dtype=torch.float32).pin_memory()
     cb_param = cbs.clone().requires_grad_(True)
 
+    side = torch.cuda.Stream()
+
     def e2e_step():
+        main = torch.cuda.current_stream()
         xd = x_h.to("cuda", non_blocking=True).requires_grad_(True)
-        tg = tgt_h.to("cuda", non_blocking=True)
         packed = ops.pack_codebooks(cb_param.detach())
+        side.wait_stream(main)
+        with torch.cuda.stream(side):                                       # eval encode + its D2H beside the training step
+            enc = ops.rq_encode(xd.detach(), cb_param.detach(), packed=packed)
+            enc_h.copy_(enc, non_blocking=True)
+        tg = tgt_h.to("cuda", non_blocking=True)
         emb, _res, ids, loss, _ll = ops.RqFunction.apply(xd, cb_param, MODE_ROT, True, beta, "auto")
         total = ((emb.sum(0) - tg) ** 2).sum(-1).mean() + loss.mean()      # h_rqvae.py:607-640 shaped consumer
         cb_param.grad = None
         total.backward()
         if comm is not None:
             comm.allreduce_async(cb_param.grad)
-        enc = ops.rq_encode(xd.detach(), cb_param.detach(), packed=packed)
         ids_h.copy_(ids, non_blocking=True)
-        enc_h.copy_(enc, non_blocking=True)
         loss_h.copy_(total.detach(), non_blocking=True)
         if comm is not None:
             comm.wait()
+        main.wait_stream(side)
+        for t_ in (xd, packed, enc):
+            t_.record_stream(side)
 
     if world > 1:
         dist.barrier()
