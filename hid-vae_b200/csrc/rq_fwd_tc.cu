@@ -46,10 +46,17 @@ constexpr int kTileRows = 128;
 constexpr int kNTile = 256;                 // codes per operand image (= accumulator columns of a slot)
 constexpr int kUnitCols = 128;              // N of one tcgen05.mma
 constexpr int kMaxSlots = 4;                // row tiles in flight per CTA (Cfg<D>::NT of them)
-constexpr int kGroupWarps = 8;              // warps of the row group == warps of the scan group
-constexpr int kThreads = 2 * kGroupWarps * 32;
-constexpr int kRowRegs = 160, kScanRegs = 96;  // setmaxnreg split of the 128-per-thread launch allocation
-static_assert(kRowRegs + kScanRegs == 256, "register hand-over must stay inside the launch allocation");
+#ifndef HV_TC_ROW_WARPS
+#define HV_TC_ROW_WARPS 8
+#endif
+constexpr int kScanWarps = 8;               // scan group: 4 lane quarters x 2 column halves (warps 0..7)
+constexpr int kRowWarps = HV_TC_ROW_WARPS;  // row group (warps 8..): 8, or 16 (more row tiles' worth of latency hiding)
+constexpr int kThreads = (kScanWarps + kRowWarps) * 32;
+// setmaxnreg split of the launch allocation (launch_bounds(kThreads, 1): 128 registers at 512 threads, 80 at 768)
+constexpr int kLaunchRegs = kRowWarps == 8 ? 128 : 80;
+constexpr int kRowRegs = kRowWarps == 8 ? 160 : 72, kScanRegs = 96;
+static_assert(kRowRegs * kRowWarps + kScanRegs * kScanWarps <= kLaunchRegs * (kRowWarps + kScanWarps),
+              "register hand-over must stay inside the launch allocation");
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 16;
 constexpr int kOnesBytes = 2 * kTileRows * 16;              // one K=16 step of the A operand: [2 chunks][128 rows][8 bf16]
@@ -354,10 +361,10 @@ __device__ __forceinline__ void scan_accumulator(uint32_t acc_addr, int h, uint3
 template <int D, bool ROT, int NSLOT>
 __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcParams p) {
   using L = Rc<D>;
-  constexpr int WPS = kGroupWarps / NSLOT;                 // warps per slot
+  constexpr int WPS = kRowWarps / NSLOT > 8 ? 8 : kRowWarps / NSLOT;  // warps per slot (at most 8: two rows per thread)
   constexpr int TPS = WPS * 32;                            // threads per slot
   constexpr int RPT = kTileRows * L::KC / TPS;             // rows per thread
-  constexpr int GC = RPT < 4 ? RPT : 4;                    // rows gathered at a time
+  constexpr int GC = kRowWarps == 16 ? (RPT < 2 ? RPT : 2) : (RPT < 4 ? RPT : 4);  // rows gathered at a time (register budget)
   extern __shared__ __align__(1024) uint8_t smem[];
   // [A slot 0 (hi | lo) | ... | ones | candidates | loss | barriers | B stages ...]   (sized for kMaxSlots slots)
   constexpr int n_slots_smem = Cfg<D>::NT;
@@ -393,8 +400,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
       ptx::mbar_init(ptx::smem_u32(&bar_b_empty[s]), NSLOT);
     }
     for (int i = 0; i < 4; ++i) ptx::mbar_init(ptx::smem_u32(&bar_mma_done[i]), 1);
-    for (int i = 0; i < 2; ++i) ptx::mbar_init(ptx::smem_u32(&bar_acc_free[i]), kGroupWarps);
-    for (int i = 0; i < kMaxSlots; ++i) ptx::mbar_init(ptx::smem_u32(&bar_scan_done[i]), kGroupWarps);
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(ptx::smem_u32(&bar_acc_free[i]), kScanWarps);
+    for (int i = 0; i < kMaxSlots; ++i) ptx::mbar_init(ptx::smem_u32(&bar_scan_done[i]), kScanWarps);
     *s_turn = 0;
     ptx::fence_mbar_init();
   }
@@ -425,11 +432,12 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
     return ((static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(k) * gridDim.x) * NSLOT + slot) * kTileRows;
   };
 
-  const int rwarp = warp - kGroupWarps;  // row group = the HIGHER warp ids: the scheduler favours them, and the
+  const int rwarp = warp - kScanWarps;  // row group = the HIGHER warp ids: the scheduler favours them, and the
                                          // row work -> MMA issue chain is the critical path of the pipeline
-  if (warp >= kGroupWarps) {
+  if (warp >= kScanWarps) {
     // =========================================== row group ====================================================
-    ptx::setmaxnreg_inc<kRowRegs>();
+    if constexpr (kRowRegs > kLaunchRegs) ptx::setmaxnreg_inc<kRowRegs>(); else ptx::setmaxnreg_dec<kRowRegs>();
+    if (rwarp < WPS * NSLOT) {  // (NSLOT = 1 with 16 row warps: the second half of the row group has no rows)
     const int slot = rwarp / WPS;
     const int ws = rwarp % WPS;  // warp inside the sub-group
     const uint32_t n_images = static_cast<uint32_t>(my_groups) * total_tiles;
@@ -668,9 +676,10 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
         }
       }
     }
+    }
   } else {
     // =========================================== scan group ===================================================
-    ptx::setmaxnreg_dec<kScanRegs>();
+    if constexpr (kScanRegs > kLaunchRegs) ptx::setmaxnreg_inc<kScanRegs>(); else ptx::setmaxnreg_dec<kScanRegs>();
     const int sw = warp;
     const int q = sw & 3;   // TMEM lane quarter
     const int h = sw >> 2;  // which 64 columns of each unit this thread scans
@@ -717,7 +726,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
     }
   }
 
-  if (ts_on && (warp == 0 || warp == kGroupWarps)) { const int who = warp == 0 ? 1 : 0; s_ts[who * 384 + 380] = ts_n; }
+  if (ts_on && (warp == 0 || warp == kScanWarps)) { const int who = warp == 0 ? 1 : 0; s_ts[who * 384 + 380] = ts_n; }
   ptx::tc_fence_before_sync();
   __syncthreads();
 #ifdef HV_TC_INSTRUMENT
@@ -756,9 +765,9 @@ int launch_slots(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* pack
   auto go = [&](auto kernel) -> int {
     cudaFuncAttributes attr;
     HV_CUDA_CHECK(cudaFuncGetAttributes(&attr, kernel));
-    if (attr.numRegs * 2 < kRowRegs + kScanRegs) {  // setmaxnreg.inc would wait forever: refuse loudly instead
+    if (attr.numRegs < kLaunchRegs) {  // setmaxnreg.inc would wait forever: refuse loudly instead
       set_error("hv_rq_forward: tcgen05 kernel was built with %d registers/thread, the register hand-over needs %d",
-                attr.numRegs, (kRowRegs + kScanRegs) / 2);
+                attr.numRegs, kLaunchRegs);
       return HV_ERR_UNSUPPORTED;
     }
     HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
