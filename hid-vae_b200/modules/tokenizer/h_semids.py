@@ -1,5 +1,6 @@
 """Bulk semantic-ID assignment with the interface of the reference's `HSemanticIdTokenizer`
-(modules/tokenizer/h_semids.py): `precompute_corpus_ids`, `cached_ids`, `exists_prefix`, `sem_ids_dim`, `reset`.
+(modules/tokenizer/h_semids.py): `precompute_corpus_ids`, `cached_ids`, `exists_prefix`, `_tokenize_seq_batch_from_cached`, `forward`, `sem_ids_dim`,
+`reset`.
 
 The reference walks the catalogue in DataLoader batches of 512, runs encode + the L-level loop, then -- in the
 concatenated / interleaved id modes the trainer uses -- runs encode + the L-level loop a SECOND time inside
@@ -13,6 +14,7 @@ from typing import List, Optional, Tuple
 import torch
 from torch import Tensor, nn
 
+from data.schemas import SeqBatch, TokenizedSeqBatch
 from hidvae_b200 import ops
 from modules.h_rqvae import HRqVae
 from modules.utils import eval_mode
@@ -182,3 +184,55 @@ class HSemanticIdTokenizer(nn.Module):
             hit = torch.cat([self._get_hits(query[i:i + BATCH_SIZE], cache).any(dim=-1)
                              for i in range(0, query.shape[0], BATCH_SIZE)]) if query.shape[0] else query.new_zeros(0, dtype=torch.bool)
         return hit.reshape(sem_id_prefix.shape[:-1]).to(sem_id_prefix.device)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # cached-id consumers: the wire format to stage 2
+    # ------------------------------------------------------------------------------------------------------------
+    def _tokenize_seq_batch_from_cached(self, ids: Tensor) -> Tensor:
+        """ids [B, N] of items -> their cached id rows laid side by side, [B, N * sem_ids_dim] (h_semids.py:241-258).
+        Ids beyond the cache read row 0, like the reference."""
+        b, n = ids.shape
+        rows = ids.to(self.cached_ids.device).reshape(-1)
+        rows = torch.where(rows >= self.cached_ids.shape[0], torch.zeros_like(rows), rows)
+        return self.cached_ids.index_select(0, rows).reshape(b, n * self.cached_ids.shape[-1])
+
+    def _ids_of_features(self, x: Tensor) -> Tensor:
+        """[M, F] item features -> [M, sem_ids_dim] id rows in the cache's column order: one encoder pass and one fused
+        L-level launch; the tag heads reuse its per-level embeddings (the reference encodes and quantises twice)."""
+        model = self.hrq_vae
+        sem_cols, tag_cols = self._columns()
+        enc = model.encode(x.to(model.device))
+        level_emb, _res, ids, _loss = model.quantize_all_levels(enc)
+        rows = torch.empty((x.shape[0], len(sem_cols) + len(tag_cols)), dtype=torch.int64, device=ids.device)
+        rows[:, sem_cols] = ids
+        if tag_cols:
+            rows[:, tag_cols] = model.predict_tags(x, level_embeddings=level_emb)["predictions"]
+        return rows
+
+    @torch.no_grad()
+    @eval_mode
+    def forward(self, batch: SeqBatch) -> TokenizedSeqBatch:
+        """SeqBatch -> TokenizedSeqBatch (h_semids.py:260-451): per sequence position the item's id row (semantic ids,
+        plus concatenated / interleaved predicted tag ids), masked positions -1, token type = column inside the row.
+        Items of the cache are gathered; when there is no cache, or an id lies beyond it, the ids are computed from the
+        batch's features (the reference's version of that branch passes a 3-D tensor to the quantiser and cannot run,
+        SURVEY.md section 8f; here the sequence is flattened to rows)."""
+        b, n = batch.ids.shape
+        use_cache = self.cached_ids is not None and not bool((batch.ids.max() >= self.cached_ids.shape[0]).item())
+        if use_cache:
+            width = self.cached_ids.shape[-1]
+            sem_ids = self._tokenize_seq_batch_from_cached(batch.ids)
+            sem_ids_fut = self._tokenize_seq_batch_from_cached(batch.ids_fut)
+        else:
+            feat = batch.x.shape[-1]
+            rows = self._ids_of_features(batch.x.reshape(b * n, feat))
+            width = rows.shape[-1]
+            sem_ids = rows.reshape(b, n * width)
+            sem_ids_fut = self._ids_of_features(batch.x_fut.reshape(b, feat)) if batch.x_fut is not None else None
+        seq_mask = None
+        if batch.seq_mask is not None:
+            seq_mask = batch.seq_mask.to(sem_ids.device).repeat_interleave(width, dim=1)
+            sem_ids = sem_ids.masked_fill(~seq_mask, -1)
+        types = torch.arange(width, device=sem_ids.device)
+        return TokenizedSeqBatch(user_ids=batch.user_ids, sem_ids=sem_ids, sem_ids_fut=sem_ids_fut, seq_mask=seq_mask,
+                                 token_type_ids=types.repeat(b, n), token_type_ids_fut=types.repeat(b, 1))

@@ -221,6 +221,43 @@ def make_hrqvae_forward_cases(ref):
     np.savez_compressed(os.path.join(OUT, "hrqvae_forward.npz"), **out)
 
 
+def make_tokenizer_cases(ref):
+    """Cached-id consumers of the reference tokenizer (modules/tokenizer/h_semids.py:197-258 and the cached branch of
+    `forward`, :366-402): rows of `cached_ids` gathered per sequence position, masked positions set to -1, token type
+    ids, `exists_prefix`.  `cached_ids` is synthetic (the methods only index it); prefix batches are multiples of the
+    reference's BATCH_SIZE = 16, the only sizes its batching loop (`ceil(n // 16)`) covers completely."""
+    from oracle.reference_shim import load_reference_tokenizer
+    T = load_reference_tokenizer()
+    S = ref.schemas
+    out = {}
+    for name, kw, width in (("plain", {}, 3), ("concat", dict(use_concatenated_ids=True, tag_class_counts=[5, 7, 9]), 6),
+                            ("interleaved", dict(use_interleaved_ids=True, tag_class_counts=[5, 7, 9]), 6)):
+        torch.manual_seed(3)
+        gen = torch.Generator().manual_seed(31)
+        tok = T.HSemanticIdTokenizer(input_dim=24, output_dim=8, hidden_dims=[16], codebook_size=16, n_layers=3,
+                                     n_cat_feats=0, tag_embed_dim=8, **kw)
+        n_items, b, n = 50, 6, 5
+        tok.cached_ids = torch.randint(0, 16, (n_items, width), generator=gen)
+        ids = torch.randint(0, n_items, (b, n), generator=gen)
+        ids_fut = torch.randint(0, n_items, (b, 1), generator=gen)
+        seq_mask = torch.rand(b, n, generator=gen) > 0.3
+        batch = S.SeqBatch(user_ids=torch.arange(b), ids=ids, ids_fut=ids_fut, x=torch.zeros(b, n, 24),
+                           x_fut=torch.zeros(b, 24), seq_mask=seq_mask)
+        res = tok(batch)
+        prefixes = torch.cat([tok.cached_ids[torch.randint(0, n_items, (24,), generator=gen), :2],
+                              torch.randint(0, 16, (24, 2), generator=gen)])           # 48 = 3 x BATCH_SIZE rows
+        full = torch.cat([tok.cached_ids[:8], torch.randint(0, 16, (8, width), generator=gen)])   # 16 rows, full width
+        out.update({f"{name}/cached_ids": _np(tok.cached_ids), f"{name}/ids": _np(ids), f"{name}/ids_fut": _np(ids_fut),
+                    f"{name}/seq_mask": _np(seq_mask), f"{name}/sem_ids": _np(res.sem_ids), f"{name}/sem_ids_fut": _np(res.sem_ids_fut),
+                    f"{name}/out_seq_mask": _np(res.seq_mask), f"{name}/token_type_ids": _np(res.token_type_ids),
+                    f"{name}/token_type_ids_fut": _np(res.token_type_ids_fut),
+                    f"{name}/from_cached": _np(tok._tokenize_seq_batch_from_cached(ids)),
+                    f"{name}/prefixes": _np(prefixes), f"{name}/prefix_hits": _np(tok.exists_prefix(prefixes)),
+                    f"{name}/full_rows": _np(full), f"{name}/full_hits": _np(tok.exists_prefix(full)),
+                    f"{name}/sem_ids_dim": np.asarray(tok.sem_ids_dim)})
+    np.savez_compressed(os.path.join(OUT, "tokenizer_cached.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order for the recorded values
@@ -232,6 +269,7 @@ def main():
     import io, contextlib
     with contextlib.redirect_stdout(io.StringIO()):
         make_hrqvae_forward_cases(ref)
+        make_tokenizer_cases(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -62,3 +62,17 @@ def load_reference():
         loss=ref_loss, quantize=ref_quantize, h_rqvae=ref_h_rqvae, kmeans=ref_kmeans, schemas=ref_schemas
     )
     return ns
+
+
+def load_reference_tokenizer():
+    """The reference's `modules/tokenizer/h_semids.py`.  It imports `data.tags_processed` for three dataset class
+    names only (that module needs polars / torch_geometric, which are not installed): a stub module with those names
+    stands in, everything the tokenizer itself computes is the reference's own code."""
+    load_reference()
+    if "data.tags_processed" not in sys.modules:
+        stub = types.ModuleType("data.tags_processed")
+        for name in ("ItemData", "SeqData", "RecDataset"):
+            setattr(stub, name, type(name, (), {}))
+        sys.modules["data.tags_processed"] = stub
+    import modules.tokenizer.h_semids as ref_tok  # noqa: E402
+    return ref_tok

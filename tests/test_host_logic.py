@@ -188,3 +188,36 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
     port = _free_port()
     mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_tokenizer_cached_consumers_match_reference_golden(golden_dir):
+    """`HSemanticIdTokenizer.forward` (cached branch), `_tokenize_seq_batch_from_cached` and `exists_prefix` against
+    outputs recorded from the reference's own class (oracle/make_golden.py::make_tokenizer_cases).  Pure indexing of
+    `cached_ids`: runs without a GPU."""
+    import numpy as np
+    import torch
+    from data.schemas import SeqBatch
+    from modules.tokenizer.h_semids import HSemanticIdTokenizer
+
+    g = np.load(os.path.join(golden_dir, "tokenizer_cached.npz"))
+    for name, kw in (("plain", {}), ("concat", dict(use_concatenated_ids=True, tag_class_counts=[5, 7, 9])),
+                     ("interleaved", dict(use_interleaved_ids=True, tag_class_counts=[5, 7, 9]))):
+        tok = HSemanticIdTokenizer(input_dim=24, output_dim=8, hidden_dims=[16], codebook_size=16, n_layers=3,
+                                   n_cat_feats=0, tag_embed_dim=8, **kw)
+        assert tok.sem_ids_dim == int(g[f"{name}/sem_ids_dim"])
+        tok.cached_ids = torch.from_numpy(g[f"{name}/cached_ids"])
+        ids, ids_fut = torch.from_numpy(g[f"{name}/ids"]), torch.from_numpy(g[f"{name}/ids_fut"])
+        mask = torch.from_numpy(g[f"{name}/seq_mask"])
+        b, n = ids.shape
+        batch = SeqBatch(user_ids=torch.arange(b), ids=ids, ids_fut=ids_fut, x=torch.zeros(b, n, 24), x_fut=torch.zeros(b, 24),
+                         seq_mask=mask)
+        out = tok(batch)
+        for key, val in (("sem_ids", out.sem_ids), ("sem_ids_fut", out.sem_ids_fut), ("out_seq_mask", out.seq_mask),
+                         ("token_type_ids", out.token_type_ids), ("token_type_ids_fut", out.token_type_ids_fut),
+                         ("from_cached", tok._tokenize_seq_batch_from_cached(ids))):
+            assert np.array_equal(val.numpy(), g[f"{name}/{key}"]), (name, key)
+        assert np.array_equal(tok.exists_prefix(torch.from_numpy(g[f"{name}/prefixes"])).numpy(), g[f"{name}/prefix_hits"])
+        assert np.array_equal(tok.exists_prefix(torch.from_numpy(g[f"{name}/full_rows"])).numpy(), g[f"{name}/full_hits"])
+        # ids beyond the cache read row 0 (h_semids.py:251-252)
+        far = torch.tensor([[0, 10 ** 6]])
+        assert torch.equal(tok._tokenize_seq_batch_from_cached(far)[0, tok.sem_ids_dim:], tok.cached_ids[0])
