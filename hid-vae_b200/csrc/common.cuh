@@ -57,6 +57,9 @@ int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* wor
                    cudaStream_t stream);
 // previous kernel generation, A/B runs only (HIDVAE_TC_IMPL=v4); `packed` = image written by launch_rq_pack
 int launch_rq_fwd_tc_v4(const RqFwdArgs& a, int d, bool rot, void* packed, cudaStream_t stream);
+// generation 10 (ticket ring): resident operand images, K <= 256, D = 16 / 32; same packed image
+int launch_rq_fwd_tc_v10(const RqFwdArgs& a, int d, bool rot, const void* packed, cudaStream_t stream);
+bool rq_fwd_tc_v10_supported(int d, int k, int n_levels);
 bool rq_fwd_tc_supported(int d, int k, int n_levels);
 size_t rq_fwd_tc_workspace_bytes(int d, int k, int n_levels);
 size_t rq_bwd_workspace_bytes(int64_t n, int d, int k, int n_levels);

@@ -812,6 +812,19 @@ bool use_v4() {
   return v4;
 }
 
+// Generation 10 (rq_fwd_tc_v10.cu).  Measured (profiles/README.md): 8-10 % faster than generation 7 on encode-only
+// launches of >= 256 Ki rows, slower on small launches and on training forwards.  HIDVAE_TC_IMPL=v10 forces it,
+// v4 / v7 keep it out (A/B runs).
+int v10_mode() {  // -1 never, 0 by size, 1 always
+  static const int mode = [] {
+    const char* e = getenv("HIDVAE_TC_IMPL");
+    if (e == nullptr || e[0] != 'v') return 0;
+    if (e[1] == '1' && e[2] == '0') return 1;
+    return (e[1] == '4' || e[1] == '7') ? -1 : 0;
+  }();
+  return mode;
+}
+
 }  // namespace
 
 bool rq_fwd_tc_supported(int d, int k, int n_levels) {
@@ -868,10 +881,17 @@ int launch_rq_fwd_tc(const RqFwdArgs& a, int d, bool rot, void* workspace, size_
   }
   if (a.n == 0) return HV_OK;
   uint8_t* packed = static_cast<uint8_t*>(workspace);
+  const bool outputs = a.emb_out != nullptr || a.loss != nullptr || a.level_loss != nullptr || a.residuals != nullptr;
+  // (generation 10 addresses a tile's ids with 32-bit offsets: row stride * 128 must fit)
+  const bool v10_ok = rq_fwd_tc_v10_supported(d, a.k, a.n_levels) && a.ids_row_stride < (1 << 23) && a.ids_row_stride > -(1 << 23);
+  if (v10_ok && (v10_mode() == 1 || (v10_mode() == 0 && !outputs && a.final_residual == nullptr && a.n >= (1 << 17)))) {
+    if (!prepacked)
+      if (int st = launch_rq_pack(a.codebooks, a.n_levels, a.k, d, workspace, workspace_bytes, stream)) return st;
+    return launch_rq_fwd_tc_v10(a, d, rot, workspace, stream);
+  }
   // Measured (profiles/README.md): the previous generation's lock-step warpgroups are still faster for D = 64
   // (streamed operand images, MMA-bound) and for large training forwards, whose heavier row work (rotation value,
   // emb_out / loss stores) is spread over 16 warps there instead of this kernel's 8 row warps.
-  const bool outputs = a.emb_out != nullptr || a.loss != nullptr || a.level_loss != nullptr || a.residuals != nullptr;
   const bool big = a.n > static_cast<int64_t>(kTileRows) * 148;
   if (use_v4() || ((d == 64 || (outputs && big)) && !use_v7_only())) {
     if (!prepacked)

@@ -20,6 +20,7 @@ ap.add_argument("--shape", default="32,256,3")
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--tag", default="")
 ap.add_argument("--encode-only", action="store_true")
+ap.add_argument("--full", action="store_true")
 args = ap.parse_args()
 d, k, L = (int(v) for v in args.shape.split(","))
 torch.cuda.set_device(0)
