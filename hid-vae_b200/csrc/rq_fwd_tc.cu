@@ -820,7 +820,16 @@ int v10_mode() {  // -1 never, 0 by size, 1 always
     const char* e = getenv("HIDVAE_TC_IMPL");
     if (e == nullptr || e[0] != 'v') return 0;
     if (e[1] == '1' && e[2] == '0') return 1;
-    return (e[1] == '4' || e[1] == '7') ? -1 : 0;
+    return (e[1] == '4' || e[1] == '7' || e[1] == '1') ? -1 : 0;
+  }();
+  return mode;
+}
+int v11_mode() {  // generation 11 (rq_fwd_tc_v11.cu): -1 never, 0 by rule, 1 always
+  static const int mode = [] {
+    const char* e = getenv("HIDVAE_TC_IMPL");
+    if (e == nullptr || e[0] != 'v') return 0;
+    if (e[1] == '1' && e[2] == '1') return 1;
+    return -1;
   }();
   return mode;
 }
@@ -835,7 +844,8 @@ bool rq_fwd_tc_supported(int d, int k, int n_levels) {
 size_t rq_fwd_tc_workspace_bytes(int d, int k, int n_levels) {
   TcPlan plan;
   if (!make_plan(d, k, n_levels, &plan)) return 0;
-  return static_cast<size_t>(n_levels) * plan.n_ktiles * plan.tile_bytes;
+  // [operand images | swizzled fp32 copy of the codebooks for generation 11 (when the shape is served)]
+  return static_cast<size_t>(n_levels) * plan.n_ktiles * plan.tile_bytes + rq_fwd_tc_v11_extra_bytes(d, k, n_levels);
 }
 
 int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* workspace, size_t workspace_bytes,
@@ -845,7 +855,8 @@ int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* wor
     set_error("hv_rq_pack_codebooks: no tcgen05 instantiation for D=%d K=%d L=%d", d, k, n_levels);
     return HV_ERR_UNSUPPORTED;
   }
-  const size_t need = static_cast<size_t>(n_levels) * plan.n_ktiles * plan.tile_bytes;
+  const size_t images = static_cast<size_t>(n_levels) * plan.n_ktiles * plan.tile_bytes;
+  const size_t need = images + rq_fwd_tc_v11_extra_bytes(d, k, n_levels);
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("hv_rq_pack_codebooks: needs a %zu-byte workspace (got %zu)", need, workspace_bytes);
     return HV_ERR_WORKSPACE;
@@ -855,6 +866,8 @@ int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* wor
     return HV_ERR_MISALIGNED;
   }
   uint8_t* packed = static_cast<uint8_t*>(workspace);
+  if (need > images)
+    if (int st = launch_rq_pack_v11(codebooks, n_levels, k, packed + images, stream)) return st;
   switch (d) {
     case 16: return pack_d<16>(codebooks, n_levels, k, plan, packed, stream);
     case 32: return pack_d<32>(codebooks, n_levels, k, plan, packed, stream);
@@ -870,7 +883,8 @@ int launch_rq_fwd_tc(const RqFwdArgs& a, int d, bool rot, void* workspace, size_
     set_error("hv_rq_forward: no tcgen05 instantiation for D=%d K=%d L=%d", d, a.k, a.n_levels);
     return HV_ERR_UNSUPPORTED;
   }
-  const size_t need = static_cast<size_t>(a.n_levels) * plan.n_ktiles * plan.tile_bytes;
+  const size_t images = static_cast<size_t>(a.n_levels) * plan.n_ktiles * plan.tile_bytes;
+  const size_t need = images + rq_fwd_tc_v11_extra_bytes(d, a.k, a.n_levels);
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("hv_rq_forward: tcgen05 path needs a %zu-byte workspace (got %zu)", need, workspace_bytes);
     return HV_ERR_WORKSPACE;
@@ -882,6 +896,11 @@ int launch_rq_fwd_tc(const RqFwdArgs& a, int d, bool rot, void* workspace, size_
   if (a.n == 0) return HV_OK;
   uint8_t* packed = static_cast<uint8_t*>(workspace);
   const bool outputs = a.emb_out != nullptr || a.loss != nullptr || a.level_loss != nullptr || a.residuals != nullptr;
+  if (need > images && v11_mode() == 1) {
+    if (!prepacked)
+      if (int st = launch_rq_pack(a.codebooks, a.n_levels, a.k, d, workspace, workspace_bytes, stream)) return st;
+    return launch_rq_fwd_tc_v11(a, rot, workspace, static_cast<const uint8_t*>(workspace) + images, stream);
+  }
   // (generation 10 addresses a tile's ids with 32-bit offsets: row stride * 128 must fit)
   const bool v10_ok = rq_fwd_tc_v10_supported(d, a.k, a.n_levels) && a.ids_row_stride < (1 << 23) && a.ids_row_stride > -(1 << 23);
   if (v10_ok && (v10_mode() == 1 || (v10_mode() == 0 && !outputs && a.final_residual == nullptr && a.n >= (1 << 17)))) {

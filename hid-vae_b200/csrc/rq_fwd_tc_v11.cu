@@ -1,0 +1,442 @@
+// tcgen05 kernel of the fused L-level residual quantiser for sm_100a -- generation 11 ("row owners").
+// D = 32, K <= 256 (one operand image per level), everything resident in shared memory.
+//
+// What the measurements of generations 7-10 showed (profiles/README.md): a (128-row tile, level) costs ~900 tensor
+// cycles and ~1050 cycles of accumulator read-out, but took 2700-3100 cycles because a level of a tile is a chain of
+// hand-overs -- A operand through shared memory + proxy fence, row group -> MMA -> scan group -> row group through
+// mbarriers, the code gather through L2 -- with only 3-4 tiles in flight.  This generation removes the hand-overs
+// instead of speeding them up:
+//
+//   OWNERSHIP  four warpgroups, each owns one row tile for its L levels; thread t of the warpgroup owns row t (= TMEM
+//              lane t) in registers from the x load to the last id.  There is no row group / scan group split, no
+//              candidate table, no second layout.
+//   A IN TMEM  the residual's bf16 hi / lo halves are written by their owner with tcgen05.st into 32 TMEM columns of
+//              the warpgroup (lane = row, two bf16 per column) and the MMAs read A from tensor memory
+//              (tcgen05.mma [d], [a], b-desc): no shared-memory A buffers, no generic->async proxy fence.
+//   GATHER     the fp32 codebooks sit in shared memory beside the bf16 operand images (216 KB for L = 3: possible
+//              because A no longer lives there), rows XOR-swizzled by 16-byte chunk, so the chosen code row is eight
+//              LDS.128 instead of a round trip to L2.
+//   TICKETS    a level is two units of 128 codes (3*D/16 tcgen05.mma from TMEM + 1 from the constant ones block, one
+//              commit each).  Three 128-column accumulators are shared by all warpgroups through tickets
+//              (shared-memory atomic, accumulator = ticket % 3), so the tensor pipe serves whichever tile is ready and
+//              the scan of unit 0 overlaps the MMAs of unit 1 and of other tiles.
+//   SCAN       by the row's owner: 2-D fold with 3-input maxima over 16-column loads (rq_fwd_tc_v10.cu), exact
+//              first-index path when a row has more than one maximiser; the id stays in a register.
+//   score[row, k] = r.c_k - |c_k|^2 / 2 with the bf16 3-way split exactly as in the other generations
+//   (modules/quantize.py:108-122); only ids (and emb_out / loss in training) leave the SM.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace hv {
+namespace {
+
+constexpr int D = 32;
+constexpr int kTileRows = 128;
+constexpr int kNTile = 256;   // codes per operand image
+constexpr int kUnitCols = 128;
+constexpr int kWGs = 4;       // row tiles in flight per CTA
+constexpr int kThreads = kWGs * 128;
+constexpr int kAccs = 3;
+constexpr int kTmemCols = 512;  // 3 x 128 accumulator columns + 4 x 32 A columns
+constexpr int kMaxLevels = 3;
+constexpr int kOnesBytes = 2 * kTileRows * 16;
+constexpr int kBarBytes = 1024;
+constexpr int kImageBytes = kNTile * (4 * D + 32);  // packed bf16 image of one level (rq_fwd_tc.cu)
+constexpr int kCbBytes = kNTile * D * 4;            // swizzled fp32 codebook of one level
+constexpr int kSmemLimit = 227 * 1024;
+#ifdef HV_TC_INSTRUMENT
+constexpr bool kInstr = true;
+#else
+constexpr bool kInstr = false;
+#endif
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // FMNMX3
+  return d;
+}
+__device__ __forceinline__ float f(uint32_t v) { return __uint_as_float(v); }
+__device__ __forceinline__ float max16(const uint32_t (&v)[16]) {
+  const float a0 = max3(f(v[0]), f(v[1]), f(v[2])), a1 = max3(f(v[3]), f(v[4]), f(v[5]));
+  const float a2 = max3(f(v[6]), f(v[7]), f(v[8])), a3 = max3(f(v[9]), f(v[10]), f(v[11]));
+  const float a4 = max3(f(v[12]), f(v[13]), f(v[14]));
+  return fmaxf(max3(a0, a1, a2), max3(a3, a4, f(v[15])));
+}
+constexpr float kBig = 1.329227995784916e36f;  // 2^120
+
+// Exact first-index (max, argmax) of one 16-column chunk against the running pair (slow path).
+__device__ __forceinline__ void scan_chunk_exact(const uint32_t (&v)[16], int base, float& best, int& best_col) {
+  const float m = max16(v);
+  if (m > best) {  // strict: an earlier chunk keeps exact ties
+    float t = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t = fmaxf(t, fmaf(f(v[j]) - m, kBig, static_cast<float>(16 - j)));
+    best = m;
+    best_col = base + 16 - static_cast<int>(t);
+  }
+}
+
+// Scan of this thread's row over the 128 columns of one accumulator at TMEM address `t0`: maximum and first column.
+__device__ __forceinline__ void scan_unit(uint32_t t0, float& m_out, int& col_out) {
+  float g[16], cm[8];
+  uint32_t a[16], b[16];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    ptx::tmem_ld_32x16(t0 + 32 * p, a);
+    ptx::tmem_ld_32x16(t0 + 32 * p + 16, b);
+    ptx::tmem_wait_ld(a, b);
+    cm[2 * p] = max16(a);
+    cm[2 * p + 1] = max16(b);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) g[j] = p == 0 ? fmaxf(f(a[j]), f(b[j])) : max3(g[j], f(a[j]), f(b[j]));
+  }
+  const float m = max3(max3(cm[0], cm[1], cm[2]), max3(cm[3], cm[4], cm[5]), fmaxf(cm[6], cm[7]));
+  // class of the maximiser: sum_j [g_j == m] * (32 + j);  chunk: sum_c [cm_c == m] * (16 + c)   (FMA pipe)
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float e = __saturatef(fmaf(g[j] - m, kBig, 1.0f));
+    s4[j & 3] = fmaf(e, static_cast<float>(32 + j), s4[j & 3]);
+  }
+  float c2[2] = {0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float e = __saturatef(fmaf(cm[c] - m, kBig, 1.0f));
+    c2[c & 1] = fmaf(e, static_cast<float>(16 + c), c2[c & 1]);
+  }
+  const float cls = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  const float chk = c2[0] + c2[1];
+  // exactly one class and one chunk attain m (all-padding units, m = -1e30, cannot win anyway; NaN takes the exact path)
+  const bool unique = (cls < 64.f && chk < 32.f) || m < -1e29f;
+  float best = m;
+  int col = 16 * (static_cast<int>(chk) - 16) + static_cast<int>(cls) - 32;
+  if (__any_sync(0xffffffffu, !unique)) {
+    best = -INFINITY;
+    col = 0;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      ptx::tmem_ld_32x16(t0 + 16 * c, a);
+      ptx::tmem_wait_ld16(a);
+      scan_chunk_exact(a, 16 * c, best, col);
+    }
+  }
+  m_out = best;
+  col_out = col;
+}
+
+// One unit (128 codes starting at code `col0` of the level's image): 3*D/16 MMAs with A from tensor memory, the norm
+// MMA with the constant ones block from shared memory, one commit.  Called by ONE elected thread.
+__device__ __forceinline__ void issue_unit(uint32_t acc, uint32_t a_tmem, uint32_t ones, uint32_t b_tile, int col0,
+                                           uint32_t bar_done) {
+  constexpr uint32_t idesc = ptx::umma_idesc_bf16(kTileRows, kUnitCols);
+  const uint32_t hi = ptx::umma_desc_hi(128);
+  constexpr uint32_t chunk_b = kNTile * 16;  // bytes between K chunks of the B image
+  constexpr uint32_t b_step = 2 * kNTile;    // one K=16 step = two chunks, in 16-byte units
+  const uint32_t b_hi = b_tile + col0 * 16;
+  const uint32_t d_bhi = ptx::umma_desc_lo(b_hi, chunk_b);
+  const uint32_t d_blo = ptx::umma_desc_lo(b_hi + (D / 8) * chunk_b, chunk_b);
+  const uint32_t d_bnrm = ptx::umma_desc_lo(b_hi + 2 * (D / 8) * chunk_b, chunk_b);
+  const uint32_t d_one = ptx::umma_desc_lo(ones, kTileRows * 16);
+  const uint32_t a_hi = a_tmem, a_lo = a_tmem + D / 2;  // D/2 columns each: two bf16 per column
+#pragma unroll
+  for (int j = 0; j < D / 16; ++j)  // r_hi . c_hi
+    ptx::umma_bf16_ts(acc, a_hi + 8 * j, ptx::umma_desc(d_bhi + j * b_step, hi), idesc, j > 0 ? 1u : 0u);
+#pragma unroll
+  for (int j = 0; j < D / 16; ++j)  // r_lo . c_hi
+    ptx::umma_bf16_ts(acc, a_lo + 8 * j, ptx::umma_desc(d_bhi + j * b_step, hi), idesc, 1u);
+#pragma unroll
+  for (int j = 0; j < D / 16; ++j)  // r_hi . c_lo
+    ptx::umma_bf16_ts(acc, a_hi + 8 * j, ptx::umma_desc(d_blo + j * b_step, hi), idesc, 1u);
+  ptx::umma_bf16(acc, ptx::umma_desc(d_one, hi), ptx::umma_desc(d_bnrm, hi), idesc, 1u);  // 1 * (-|c|^2 / 2)
+  ptx::umma_commit(bar_done);
+}
+
+// swizzled fp32 copy of the codebooks for the in-kernel gather: chunk c (16 bytes) of code k sits at chunk c ^ (k & 7)
+__global__ void rq_pack_fp32_kernel(const float* __restrict__ codebooks, int n_levels, int k, uint8_t* __restrict__ dst) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (level, code, chunk)
+  if (idx >= n_levels * kNTile * 8) return;
+  const int c = idx & 7, code = (idx >> 3) % kNTile, level = idx / (8 * kNTile);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (code < k) v = *reinterpret_cast<const float4*>(codebooks + (static_cast<int64_t>(level) * k + code) * D + c * 4);
+  *reinterpret_cast<float4*>(dst + static_cast<size_t>(level) * kCbBytes + code * (D * 4) + ((c ^ (code & 7)) << 4)) = v;
+}
+
+struct V11Params {
+  const uint8_t* images;  // [L] packed bf16 images
+  const uint8_t* cb32;    // [L] swizzled fp32 codebooks
+  int debug;
+};
+
+template <bool ROT>
+__global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a, V11Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // [ones | barriers + counters | operand images (L) | fp32 codebooks (L)]
+  uint8_t* s_ones = smem;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kOnesBytes);
+  uint8_t* s_img = smem + kOnesBytes + kBarBytes;
+  uint8_t* s_cb = s_img + a.n_levels * kImageBytes;
+
+  uint64_t* bar_b_full = s_bar;                      // [kMaxLevels]  TMA -> everybody (images + codebooks of a level)
+  uint64_t* bar_mma_done = bar_b_full + kMaxLevels;  // [kAccs]  MMA completion -> the owning warpgroup
+  // Progress COUNTERS, not phase parities: with two tickets per warpgroup up to eight tickets are outstanding, so a
+  // waiter can be two uses of an accumulator ahead of its barrier, where a parity test would pass too early.
+  uint32_t* s_free = reinterpret_cast<uint32_t*>(bar_mma_done + kAccs);  // [kAccs]  warps that finished scanning it
+  uint32_t* s_issued = s_free + kAccs;               // [kWGs]   units the warpgroup's issuer has committed
+  uint32_t* s_ticket = s_issued + kWGs;
+  uint32_t* s_tk = s_ticket + 1;                     // [kWGs][2]  first ticket of the warpgroup's level (double-buffered)
+  uint32_t* s_tmem = s_tk + 2 * kWGs;
+  uint32_t* s_ts = s_tmem + 1;                       // [192] timestamps of block 0, warpgroup 0 (instrumented builds)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wg = warp >> 2;
+  const int q = warp & 3;        // TMEM lane quarter of this warp
+  const int t = q * 32 + lane;   // the thread's row of the tile == its TMEM lane
+  const int n_levels = a.n_levels;
+  int ts_n = 0;
+  const bool ts_on = kInstr && (p.debug & 64) && blockIdx.x == 0 && threadIdx.x == 0;
+  auto stamp = [&](int code) {
+    if (ts_on && ts_n < 90) {
+      s_ts[2 * ts_n] = code;
+      s_ts[2 * ts_n + 1] = static_cast<uint32_t>(clock64());
+      ++ts_n;
+    }
+  };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxLevels; ++i) ptx::mbar_init(ptx::smem_u32(&bar_b_full[i]), 1);
+    for (int i = 0; i < kAccs; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bar_mma_done[i]), 1);
+      s_free[i] = 0;
+    }
+    for (int i = 0; i < kWGs; ++i) s_issued[i] = 0;
+    *s_ticket = 0;
+    ptx::fence_mbar_init();
+    for (int l = 0; l < n_levels; ++l) {  // resident for the whole kernel
+      const uint32_t bar = ptx::smem_u32(&bar_b_full[l]);
+      ptx::mbar_arrive_expect_tx(bar, kImageBytes + kCbBytes);
+      ptx::bulk_g2s(ptx::smem_u32(s_img + l * kImageBytes), p.images + static_cast<size_t>(l) * kImageBytes, kImageBytes, bar);
+      ptx::bulk_g2s(ptx::smem_u32(s_cb + l * kCbBytes), p.cb32 + static_cast<size_t>(l) * kCbBytes, kCbBytes, bar);
+    }
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(s_tmem), kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + kTileRows) {
+    // constant A block that multiplies the norm pieces: row -> [1, 1, 1, 0, 0, 0, 0, 0 | 0 x 8]
+    const int i = threadIdx.x - 128;
+    *reinterpret_cast<uint4*>(s_ones + i * 16) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
+    *reinterpret_cast<uint4*>(s_ones + kTileRows * 16 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async_smem();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
+  const uint32_t a_tmem = tmem_base + kAccs * kUnitCols + wg * D;  // the warpgroup's A operand: hi (16 columns) | lo (16)
+  const uint32_t ones = ptx::smem_u32(s_ones);
+  const uint32_t bar_wg = 1 + wg;
+
+  const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
+  const int my_tiles = static_cast<int>((n_row_tiles - 1 - blockIdx.x) / gridDim.x + 1);  // grid <= n_row_tiles
+  auto tile_row0 = [&](int i) -> int64_t { return (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x) * kTileRows; };
+  const bool want_loss = a.loss != nullptr || a.level_loss != nullptr;
+  // the last level's code row is only needed when something other than ids is asked for
+  const bool tail_last = a.emb_out != nullptr || want_loss || a.final_residual != nullptr;
+
+  float r[D];
+  auto load_x = [&](int i) {  // the thread's row of this CTA's i-th tile (rows beyond n read as zero)
+    const int64_t grow = tile_row0(i) + t;
+    if (grow < a.n) {
+      load_row<D>(r, a.x + grow * D);
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) r[d] = 0.f;
+    }
+  };
+
+  bool have_x = false;
+  uint32_t lvl = 0;  // levels done by this warpgroup (selects the s_tk buffer)
+  for (int i = wg; i < my_tiles; i += kWGs) {
+    const int64_t grow = tile_row0(i) + t;
+    const bool valid = grow < a.n;
+    if (q == 0 && lane == 0 && i + kWGs < my_tiles) {  // pull the warpgroup's next tile into L2
+      const int64_t next0 = tile_row0(i + kWGs);
+      const int64_t rows = a.n - next0 < kTileRows ? a.n - next0 : kTileRows;
+      ptx::bulk_prefetch_l2(a.x + next0 * D, static_cast<uint32_t>(rows * D * 4));
+    }
+    stamp(1);
+    if (!have_x) load_x(i);
+    have_x = false;
+    float loss = 0.f;
+
+    for (int l = 0; l < n_levels; ++l, ++lvl) {
+      const bool last = l + 1 == n_levels;
+      const bool tail = !last || tail_last;
+      stamp(2);
+      if (a.residuals != nullptr && valid) store_row<D>(a.residuals + (static_cast<int64_t>(l) * a.n + grow) * D, r);
+      // ---- the residual's bf16 hi | lo halves -> the warpgroup's A columns in tensor memory ----
+      {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float x0 = r[2 * j], x1 = r[2 * j + 1];
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+          const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hh);
+          const float h0 = __uint_as_float(hw << 16), h1 = __uint_as_float(hw & 0xFFFF0000u);
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+          hi[j] = hw;
+          lo[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        ptx::tmem_st_32x16(a_tmem + lane_bits, hi);
+        ptx::tmem_st_32x16(a_tmem + lane_bits + 16, lo);
+        ptx::tmem_wait_st();
+      }
+      ptx::tc_fence_before_sync();
+      if (q == 0 && lane == 0) s_tk[2 * wg + (lvl & 1)] = atomicAdd(s_ticket, 2u);  // two units = two accumulators
+      ptx::named_bar_sync(bar_wg, 128);
+      const uint32_t t0 = *reinterpret_cast<volatile uint32_t*>(&s_tk[2 * wg + (lvl & 1)]);
+      ptx::tc_fence_after_sync();
+      stamp(3);
+      if (q == 0) {
+        if (ptx::elect_one()) {
+          if (i < kWGs) ptx::mbar_wait(ptx::smem_u32(&bar_b_full[l]), 0u);  // loaded once: only a first tile can be early
+          const uint32_t b_tile = ptx::smem_u32(s_img + l * kImageBytes);
+#pragma unroll
+          for (uint32_t u = 0; u < 2; ++u) {
+            const uint32_t tk = t0 + u, acc = tk % kAccs, use = tk / kAccs;
+            ptx::counter_wait(ptx::smem_u32(&s_free[acc]), 4u * use);  // every earlier use of the accumulator is scanned
+            ptx::tc_fence_after_sync();
+            issue_unit(tmem_base + acc * kUnitCols, a_tmem, ones, b_tile, u * kUnitCols, ptx::smem_u32(&bar_mma_done[acc]));
+            ptx::counter_add_release(ptx::smem_u32(&s_issued[wg]), 1u);
+          }
+        }
+        __syncwarp();
+      }
+      stamp(4);
+      if (last && !tail && i + kWGs < my_tiles) {  // encode: the row is dead now -- the next tile's travels behind the MMAs
+        load_x(i + kWGs);
+        have_x = true;
+      }
+      if (i < kWGs) ptx::mbar_wait(ptx::smem_u32(&bar_b_full[l]), 0u);  // (the gather reads the level's codebook)
+
+      // ---- the owner scans its row in both units ----
+      float best = -INFINITY;
+      int col = 0;
+#pragma unroll
+      for (uint32_t u = 0; u < 2; ++u) {
+        const uint32_t tk = t0 + u, acc = tk % kAccs, use = tk / kAccs;
+        if (lane == 0) ptx::counter_wait(ptx::smem_u32(&s_issued[wg]), 2u * lvl + u + 1u);  // issued: the parity is now exact
+        __syncwarp();
+        ptx::mbar_wait(ptx::smem_u32(&bar_mma_done[acc]), use & 1u);
+        ptx::tc_fence_after_sync();
+        if (u == 0) stamp(5);
+        float m;
+        int c;
+        scan_unit(tmem_base + acc * kUnitCols + lane_bits, m, c);
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::counter_add_release(ptx::smem_u32(&s_free[acc]), 1u);
+        if (m > best) {  // strict: the lower unit keeps exact ties
+          best = m;
+          col = c + static_cast<int>(u) * kUnitCols;
+        }
+      }
+      stamp(6);
+      const uint32_t k_sel = static_cast<uint32_t>(col) < static_cast<uint32_t>(a.k) ? static_cast<uint32_t>(col)
+                                                                                    : static_cast<uint32_t>(a.k - 1);
+      if (valid) a.ids[grow * a.ids_row_stride + l * a.ids_level_stride] = k_sel;
+      if (tail) {
+        // ---- the chosen fp32 code row from shared memory (chunk c of code k sits at chunk c ^ (k & 7)) ----
+        float e[D];
+        const uint32_t row_addr = ptx::smem_u32(s_cb + l * kCbBytes) + k_sel * (D * 4);
+        const uint32_t sw = k_sel & 7u;
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) {
+          const float4 v = ptx::lds128(row_addr + ((c ^ sw) << 4));
+          e[4 * c] = v.x, e[4 * c + 1] = v.y, e[4 * c + 2] = v.z, e[4 * c + 3] = v.w;
+        }
+        if (tail_last) {  // something besides ids is wanted: value / loss / outputs (modules/quantize.py:131-148)
+          float* o_out = (valid && a.emb_out != nullptr) ? a.emb_out + (static_cast<int64_t>(l) * a.n + grow) * D : nullptr;
+          const float ll = rq_level_tail<D, ROT>(r, e, a.beta, o_out);
+          loss += ll;
+          if (valid) {
+            if (a.level_loss != nullptr) a.level_loss[static_cast<int64_t>(l) * a.n + grow] = ll;
+            if (last && a.loss != nullptr) a.loss[grow] = loss;
+            if (last && a.final_residual != nullptr) store_row<D>(a.final_residual + grow * D, r);
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < D; ++d) r[d] = r[d] - e[d];
+        }
+      }
+      stamp(7);
+    }
+  }
+
+  if (ts_on) s_ts[190] = ts_n;
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+#ifdef HV_TC_INSTRUMENT
+  if ((p.debug & 64) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int n = s_ts[190];
+    for (int i = 0; i < n; ++i) printf("TS 0 %u %u\n", s_ts[2 * i], s_ts[2 * i + 1]);
+  }
+#endif
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+int smem_bytes(int n_levels) { return kOnesBytes + kBarBytes + n_levels * (kImageBytes + kCbBytes); }
+
+}  // namespace
+
+bool rq_fwd_tc_v11_supported(int d, int k, int n_levels) {
+  return d == D && k >= 1 && k <= kNTile && n_levels >= 1 && n_levels <= kMaxLevels && smem_bytes(n_levels) <= kSmemLimit;
+}
+
+// bytes of the swizzled fp32 codebook copy that follows the operand images in the workspace (0: shape not served)
+size_t rq_fwd_tc_v11_extra_bytes(int d, int k, int n_levels) {
+  return rq_fwd_tc_v11_supported(d, k, n_levels) ? static_cast<size_t>(n_levels) * kCbBytes : 0;
+}
+
+int launch_rq_pack_v11(const float* codebooks, int n_levels, int k, void* dst, cudaStream_t stream) {
+  const int total = n_levels * kNTile * 8;
+  rq_pack_fp32_kernel<<<(total + 255) / 256, 256, 0, stream>>>(codebooks, n_levels, k, static_cast<uint8_t*>(dst));
+  HV_CUDA_CHECK(cudaGetLastError());
+  return HV_OK;
+}
+
+// `images` = operand images written by launch_rq_pack, `cb32` = the copy written by launch_rq_pack_v11
+int launch_rq_fwd_tc_v11(const RqFwdArgs& a, bool rot, const void* images, const void* cb32, cudaStream_t stream) {
+  if (!rq_fwd_tc_v11_supported(D, a.k, a.n_levels)) {
+    set_error("hv_rq_forward: no generation-11 tcgen05 instantiation for K=%d L=%d", a.k, a.n_levels);
+    return HV_ERR_UNSUPPORTED;
+  }
+  if (a.n == 0) return HV_OK;
+  DeviceProps props;
+  if (int st = device_props(&props)) return st;
+  const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
+  const unsigned grid = static_cast<unsigned>(n_row_tiles < props.sm_count ? n_row_tiles : props.sm_count);
+  static const int debug = [] {
+    const char* e = getenv("HIDVAE_TC_DEBUG");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  V11Params p{static_cast<const uint8_t*>(images), static_cast<const uint8_t*>(cb32), debug};
+  const int smem = smem_bytes(a.n_levels);
+  auto go = [&](auto kernel) -> int {
+    HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kernel<<<grid, kThreads, smem, stream>>>(a, p);
+    HV_CUDA_CHECK(cudaGetLastError());
+    return HV_OK;
+  };
+  return rot ? go(rq_fwd_tc_v11_kernel<true>) : go(rq_fwd_tc_v11_kernel<false>);
+}
+
+}  // namespace hv
