@@ -62,7 +62,6 @@ int launch_rq_fwd_tc_v10(const RqFwdArgs& a, int d, bool rot, const void* packed
 bool rq_fwd_tc_v10_supported(int d, int k, int n_levels);
 // generation 11 (row owners): D = 32, K <= 256, A operand in tensor memory, fp32 codebooks in shared memory
 int launch_rq_fwd_tc_v11(const RqFwdArgs& a, bool rot, const void* images, const void* cb32, cudaStream_t stream);
-int launch_rq_pack_v11(const float* codebooks, int n_levels, int k, void* dst, cudaStream_t stream);
 bool rq_fwd_tc_v11_supported(int d, int k, int n_levels);
 size_t rq_fwd_tc_v11_extra_bytes(int d, int k, int n_levels);
 bool rq_fwd_tc_supported(int d, int k, int n_levels);

@@ -112,9 +112,11 @@ bool make_plan(int d, int k, int n_levels, TcPlan* p) {
 //   [c_hi : D/8 chunks][c_lo : D/8 chunks][norm : 2 chunks], chunk = [256 codes][8 bf16] (16 B per code)
 // Padded codes (index >= K) get zero vectors and a -1e30 norm term so they can never win the argmax.
 // ---------------------------------------------------------------------------------------------------------
+// `cb32` (optional, D = 32 with one image per level): the swizzled fp32 copy generation 11 gathers from -- chunk c
+// (16 bytes) of code k at chunk c ^ (k & 7) of its 128-byte row, [L][256 codes][32 floats].
 template <int D>
 __global__ void rq_pack_codebooks_kernel(const float* __restrict__ codebooks, int n_levels, int k, int n_ktiles,
-                                         int tile_bytes, uint8_t* __restrict__ packed) {
+                                         int tile_bytes, uint8_t* __restrict__ packed, uint8_t* __restrict__ cb32) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (level, image, code in image)
   const int total = n_levels * n_ktiles * kNTile;
   if (idx >= total) return;
@@ -136,6 +138,14 @@ __global__ void rq_pack_codebooks_kernel(const float* __restrict__ codebooks, in
   } else {
 #pragma unroll
     for (int i = 0; i < D; ++i) v[i] = 0.f;
+  }
+  if constexpr (D == 32) {
+    if (cb32 != nullptr) {
+      uint8_t* row = cb32 + (static_cast<size_t>(level) * kNTile + c) * (D * 4);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        *reinterpret_cast<float4*>(row + ((ch ^ (c & 7)) << 4)) = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+    }
   }
   float cc = 0.f;
 #pragma unroll
@@ -744,10 +754,11 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_kernel(RqFwdArgs a, TcP
 }
 
 template <int D>
-int pack_d(const float* codebooks, int n_levels, int k, const TcPlan& plan, uint8_t* packed, cudaStream_t stream) {
+int pack_d(const float* codebooks, int n_levels, int k, const TcPlan& plan, uint8_t* packed, cudaStream_t stream,
+           uint8_t* cb32 = nullptr) {
   const int total_codes = n_levels * plan.n_ktiles * kNTile;
   rq_pack_codebooks_kernel<D><<<(total_codes + 127) / 128, 128, 0, stream>>>(codebooks, n_levels, k, plan.n_ktiles,
-                                                                           plan.tile_bytes, packed);
+                                                                           plan.tile_bytes, packed, cb32);
   HV_CUDA_CHECK(cudaGetLastError());
   return HV_OK;
 }
@@ -866,11 +877,9 @@ int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* wor
     return HV_ERR_MISALIGNED;
   }
   uint8_t* packed = static_cast<uint8_t*>(workspace);
-  if (need > images)
-    if (int st = launch_rq_pack_v11(codebooks, n_levels, k, packed + images, stream)) return st;
   switch (d) {
     case 16: return pack_d<16>(codebooks, n_levels, k, plan, packed, stream);
-    case 32: return pack_d<32>(codebooks, n_levels, k, plan, packed, stream);
+    case 32: return pack_d<32>(codebooks, n_levels, k, plan, packed, stream, need > images ? packed + images : nullptr);
     case 64: return pack_d<64>(codebooks, n_levels, k, plan, packed, stream);
     default: return HV_ERR_UNSUPPORTED;
   }
@@ -896,7 +905,9 @@ int launch_rq_fwd_tc(const RqFwdArgs& a, int d, bool rot, void* workspace, size_
   if (a.n == 0) return HV_OK;
   uint8_t* packed = static_cast<uint8_t*>(workspace);
   const bool outputs = a.emb_out != nullptr || a.loss != nullptr || a.level_loss != nullptr || a.residuals != nullptr;
-  if (need > images && v11_mode() == 1) {
+  // Generation 11 (rq_fwd_tc_v11.cu) serves every shape it supports (D = 32, K <= 256, L <= 3): measured faster than
+  // generations 4 / 7 / 10 on encode and training forwards from 12 K to 4 Mi rows (profiles/README.md).
+  if (need > images && v11_mode() >= 0) {
     if (!prepacked)
       if (int st = launch_rq_pack(a.codebooks, a.n_levels, a.k, d, workspace, workspace_bytes, stream)) return st;
     return launch_rq_fwd_tc_v11(a, rot, workspace, static_cast<const uint8_t*>(workspace) + images, stream);

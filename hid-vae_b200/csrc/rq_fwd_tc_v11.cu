@@ -16,10 +16,13 @@
 //   GATHER     the fp32 codebooks sit in shared memory beside the bf16 operand images (216 KB for L = 3: possible
 //              because A no longer lives there), rows XOR-swizzled by 16-byte chunk, so the chosen code row is eight
 //              LDS.128 instead of a round trip to L2.
-//   TICKETS    a level is two units of 128 codes (3*D/16 tcgen05.mma from TMEM + 1 from the constant ones block, one
-//              commit each).  Three 128-column accumulators are shared by all warpgroups through tickets
-//              (shared-memory atomic, accumulator = ticket % 3), so the tensor pipe serves whichever tile is ready and
-//              the scan of unit 0 overlaps the MMAs of unit 1 and of other tiles.
+//   ISSUER     a level is two units of 128 codes (3*D/16 tcgen05.mma from TMEM + 1 from the constant ones block, one
+//              commit each).  A tcgen05.mma takes as long to issue as the previous one takes to execute (measured: 80
+//              cycles each), so a seventeenth warp does nothing else: warpgroups queue "level staged" requests, the
+//              issuer serves them first come first served, giving every unit the next of three 128-column accumulators
+//              (unit number % 3) as soon as its previous user has been scanned.  The scan of unit 0 overlaps the MMAs
+//              of unit 1 and of other tiles, and no scanning warp ever waits inside an issue loop (which, with the
+//              owners issuing for themselves, held accumulators hostage: measured 9000 cycles per level).
 //   SCAN       by the row's owner: 2-D fold with 3-input maxima over 16-column loads (rq_fwd_tc_v10.cu), exact
 //              first-index path when a row has more than one maximiser; the id stays in a register.
 //   score[row, k] = r.c_k - |c_k|^2 / 2 with the bf16 3-way split exactly as in the other generations
@@ -36,8 +39,20 @@ constexpr int D = 32;
 constexpr int kTileRows = 128;
 constexpr int kNTile = 256;   // codes per operand image
 constexpr int kUnitCols = 128;
-constexpr int kWGs = 4;       // row tiles in flight per CTA
-constexpr int kThreads = kWGs * 128;
+#ifndef HV_V11_WGS
+#define HV_V11_WGS 3  // measured: three owners at 128 registers beat four at 112 (spills)
+#endif
+constexpr int kWGs = HV_V11_WGS;  // row tiles in flight per CTA (owner warpgroups)
+constexpr int kIssuerWarp = kWGs * 4;   // the warp after the owners issues every tcgen05.mma
+constexpr int kThreads = (kWGs + 1) * 128;  // (register allocation is per warpgroup: the issuer's three siblings idle)
+// four owners: launch 96, owners take 112, the issuer's warpgroup keeps 24; three owners: 128 for everybody
+#ifndef HV_V11_OWNER_REGS
+#define HV_V11_OWNER_REGS 128
+#endif
+constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8;
+constexpr int kOwnerRegs = kWGs == 4 ? 112 : HV_V11_OWNER_REGS, kIssuerRegs = kWGs == 4 ? 24 : (HV_V11_OWNER_REGS > 128 ? 24 : 128);
+static_assert(kWGs * 128 * kOwnerRegs + 128 * kIssuerRegs <= kThreads * kLaunchRegs, "register hand-over must stay inside the launch allocation");
+constexpr int kQueue = 8;               // staged (warpgroup, level) requests waiting for the issuer
 constexpr int kAccs = 3;
 constexpr int kTmemCols = 512;  // 3 x 128 accumulator columns + 4 x 32 A columns
 constexpr int kMaxLevels = 3;
@@ -153,16 +168,6 @@ __device__ __forceinline__ void issue_unit(uint32_t acc, uint32_t a_tmem, uint32
   ptx::umma_commit(bar_done);
 }
 
-// swizzled fp32 copy of the codebooks for the in-kernel gather: chunk c (16 bytes) of code k sits at chunk c ^ (k & 7)
-__global__ void rq_pack_fp32_kernel(const float* __restrict__ codebooks, int n_levels, int k, uint8_t* __restrict__ dst) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (level, code, chunk)
-  if (idx >= n_levels * kNTile * 8) return;
-  const int c = idx & 7, code = (idx >> 3) % kNTile, level = idx / (8 * kNTile);
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (code < k) v = *reinterpret_cast<const float4*>(codebooks + (static_cast<int64_t>(level) * k + code) * D + c * 4);
-  *reinterpret_cast<float4*>(dst + static_cast<size_t>(level) * kCbBytes + code * (D * 4) + ((c ^ (code & 7)) << 4)) = v;
-}
-
 struct V11Params {
   const uint8_t* images;  // [L] packed bf16 images
   const uint8_t* cb32;    // [L] swizzled fp32 codebooks
@@ -183,9 +188,10 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
   // Progress COUNTERS, not phase parities: with two tickets per warpgroup up to eight tickets are outstanding, so a
   // waiter can be two uses of an accumulator ahead of its barrier, where a parity test would pass too early.
   uint32_t* s_free = reinterpret_cast<uint32_t*>(bar_mma_done + kAccs);  // [kAccs]  warps that finished scanning it
-  uint32_t* s_issued = s_free + kAccs;               // [kWGs]   units the warpgroup's issuer has committed
-  uint32_t* s_ticket = s_issued + kWGs;
-  uint32_t* s_tk = s_ticket + 1;                     // [kWGs][2]  first ticket of the warpgroup's level (double-buffered)
+  uint32_t* s_issued = s_free + kAccs;               // [kWGs]   units of the warpgroup the issuer has committed
+  uint32_t* s_qtail = s_issued + kWGs;               // requests pushed so far
+  uint32_t* s_q = s_qtail + 1;                       // [kQueue] (sequence + 1) << 8 | level << 4 | warpgroup
+  uint32_t* s_tk = s_q + kQueue;                     // [kWGs][2]  first unit number of the warpgroup's level (double-buffered)
   uint32_t* s_tmem = s_tk + 2 * kWGs;
   uint32_t* s_ts = s_tmem + 1;                       // [192] timestamps of block 0, warpgroup 0 (instrumented builds)
 
@@ -212,7 +218,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
       s_free[i] = 0;
     }
     for (int i = 0; i < kWGs; ++i) s_issued[i] = 0;
-    *s_ticket = 0;
+    for (int i = 0; i < kQueue; ++i) s_q[i] = 0;
+    *s_qtail = 0;
     ptx::fence_mbar_init();
     for (int l = 0; l < n_levels; ++l) {  // resident for the whole kernel
       const uint32_t bar = ptx::smem_u32(&bar_b_full[l]);
@@ -248,6 +255,44 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
   // the last level's code row is only needed when something other than ids is asked for
   const bool tail_last = a.emb_out != nullptr || want_loss || a.final_residual != nullptr;
 
+  if (warp >= kIssuerWarp) {
+    // =========================================== MMA issuer ===================================================
+    if constexpr (kIssuerRegs < kLaunchRegs) ptx::setmaxnreg_dec<kIssuerRegs>();
+    if (warp == kIssuerWarp && ptx::elect_one()) {
+      // One request per staged level, both units back to back.  (Requesting unit 1 only when the scan of unit 0 starts,
+      // so that its accumulator is not parked full meanwhile, measured slower: 0.81 vs 0.75 ms at 4 Mi rows.)
+      const uint32_t n_req = static_cast<uint32_t>(my_tiles) * static_cast<uint32_t>(n_levels);
+      uint32_t unit = 0;  // units issued so far: accumulator = unit % 3, its use number = unit / 3
+      for (uint32_t s = 0; s < n_req; ++s) {
+        const uint32_t q_addr = ptx::smem_u32(&s_q[s % kQueue]);
+        uint32_t qv = ptx::counter_ld_acquire(q_addr);
+        if ((qv >> 8) != s + 1u) {
+          const long long t_start = clock64();
+          while (((qv = ptx::counter_ld_acquire(q_addr)) >> 8) != s + 1u) {
+            if (clock64() - t_start > 4000000000LL) {
+              printf("hidvae_b200: issuer request wait timed out (block %d request %u)\n", blockIdx.x, s);
+              __trap();
+            }
+          }
+        }
+        const uint32_t rwg = qv & 0xFu, l = (qv >> 4) & 0xFu;
+        if (s < static_cast<uint32_t>(kWGs * n_levels)) ptx::mbar_wait(ptx::smem_u32(&bar_b_full[l]), 0u);  // images are loaded once
+        s_tk[2 * rwg + ((s_issued[rwg] >> 1) & 1u)] = unit;  // (only this thread writes s_issued: a plain read is exact)
+        const uint32_t b_tile = ptx::smem_u32(s_img + l * kImageBytes);
+        const uint32_t ra_tmem = tmem_base + kAccs * kUnitCols + rwg * D;
+#pragma unroll
+        for (uint32_t u = 0; u < 2; ++u, ++unit) {
+          const uint32_t acc = unit % kAccs, use = unit / kAccs;
+          ptx::counter_wait(ptx::smem_u32(&s_free[acc]), 4u * use);  // every earlier use of the accumulator is scanned
+          ptx::tc_fence_after_sync();
+          issue_unit(tmem_base + acc * kUnitCols, ra_tmem, ones, b_tile, u * kUnitCols, ptx::smem_u32(&bar_mma_done[acc]));
+          ptx::counter_add_release(ptx::smem_u32(&s_issued[rwg]), 1u);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+  if constexpr (kOwnerRegs > kLaunchRegs) ptx::setmaxnreg_inc<kOwnerRegs>();
   float r[D];
   auto load_x = [&](int i) {  // the thread's row of this CTA's i-th tile (rows beyond n read as zero)
     const int64_t grow = tile_row0(i) + t;
@@ -264,11 +309,13 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
   for (int i = wg; i < my_tiles; i += kWGs) {
     const int64_t grow = tile_row0(i) + t;
     const bool valid = grow < a.n;
+#ifndef HV_V11_NO_PREFETCH
     if (q == 0 && lane == 0 && i + kWGs < my_tiles) {  // pull the warpgroup's next tile into L2
       const int64_t next0 = tile_row0(i + kWGs);
       const int64_t rows = a.n - next0 < kTileRows ? a.n - next0 : kTileRows;
       ptx::bulk_prefetch_l2(a.x + next0 * D, static_cast<uint32_t>(rows * D * 4));
     }
+#endif
     stamp(1);
     if (!have_x) load_x(i);
     have_x = false;
@@ -297,26 +344,14 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
         ptx::tmem_wait_st();
       }
       ptx::tc_fence_before_sync();
-      if (q == 0 && lane == 0) s_tk[2 * wg + (lvl & 1)] = atomicAdd(s_ticket, 2u);  // two units = two accumulators
       ptx::named_bar_sync(bar_wg, 128);
-      const uint32_t t0 = *reinterpret_cast<volatile uint32_t*>(&s_tk[2 * wg + (lvl & 1)]);
-      ptx::tc_fence_after_sync();
-      stamp(3);
-      if (q == 0) {
-        if (ptx::elect_one()) {
-          if (i < kWGs) ptx::mbar_wait(ptx::smem_u32(&bar_b_full[l]), 0u);  // loaded once: only a first tile can be early
-          const uint32_t b_tile = ptx::smem_u32(s_img + l * kImageBytes);
-#pragma unroll
-          for (uint32_t u = 0; u < 2; ++u) {
-            const uint32_t tk = t0 + u, acc = tk % kAccs, use = tk / kAccs;
-            ptx::counter_wait(ptx::smem_u32(&s_free[acc]), 4u * use);  // every earlier use of the accumulator is scanned
-            ptx::tc_fence_after_sync();
-            issue_unit(tmem_base + acc * kUnitCols, a_tmem, ones, b_tile, u * kUnitCols, ptx::smem_u32(&bar_mma_done[acc]));
-            ptx::counter_add_release(ptx::smem_u32(&s_issued[wg]), 1u);
-          }
-        }
-        __syncwarp();
+      if (q == 0 && lane == 0) {  // the level is staged: queue it for the issuer
+        const uint32_t sq = atomicAdd(s_qtail, 1u);
+        asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(ptx::smem_u32(&s_q[sq % kQueue])),
+                     "r"(((sq + 1u) << 8) | (static_cast<uint32_t>(l) << 4) | static_cast<uint32_t>(wg))
+                     : "memory");
       }
+      stamp(3);
       stamp(4);
       if (last && !tail && i + kWGs < my_tiles) {  // encode: the row is dead now -- the next tile's travels behind the MMAs
         load_x(i + kWGs);
@@ -329,9 +364,9 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
       int col = 0;
 #pragma unroll
       for (uint32_t u = 0; u < 2; ++u) {
-        const uint32_t tk = t0 + u, acc = tk % kAccs, use = tk / kAccs;
         if (lane == 0) ptx::counter_wait(ptx::smem_u32(&s_issued[wg]), 2u * lvl + u + 1u);  // issued: the parity is now exact
         __syncwarp();
+        const uint32_t tk = *reinterpret_cast<volatile uint32_t*>(&s_tk[2 * wg + (lvl & 1)]) + u, acc = tk % kAccs, use = tk / kAccs;
         ptx::mbar_wait(ptx::smem_u32(&bar_mma_done[acc]), use & 1u);
         ptx::tc_fence_after_sync();
         if (u == 0) stamp(5);
@@ -379,6 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
   }
 
   if (ts_on) s_ts[190] = ts_n;
+  }  // row owners
   ptx::tc_fence_before_sync();
   __syncthreads();
 #ifdef HV_TC_INSTRUMENT
@@ -406,14 +442,8 @@ size_t rq_fwd_tc_v11_extra_bytes(int d, int k, int n_levels) {
   return rq_fwd_tc_v11_supported(d, k, n_levels) ? static_cast<size_t>(n_levels) * kCbBytes : 0;
 }
 
-int launch_rq_pack_v11(const float* codebooks, int n_levels, int k, void* dst, cudaStream_t stream) {
-  const int total = n_levels * kNTile * 8;
-  rq_pack_fp32_kernel<<<(total + 255) / 256, 256, 0, stream>>>(codebooks, n_levels, k, static_cast<uint8_t*>(dst));
-  HV_CUDA_CHECK(cudaGetLastError());
-  return HV_OK;
-}
-
-// `images` = operand images written by launch_rq_pack, `cb32` = the copy written by launch_rq_pack_v11
+// `images` = operand images, `cb32` = swizzled fp32 copy of the codebooks (chunk c of code k at chunk c ^ (k & 7)), both
+// written by launch_rq_pack
 int launch_rq_fwd_tc_v11(const RqFwdArgs& a, bool rot, const void* images, const void* cb32, cudaStream_t stream) {
   if (!rq_fwd_tc_v11_supported(D, a.k, a.n_levels)) {
     set_error("hv_rq_forward: no generation-11 tcgen05 instantiation for K=%d L=%d", a.k, a.n_levels);
@@ -431,6 +461,13 @@ int launch_rq_fwd_tc_v11(const RqFwdArgs& a, bool rot, const void* images, const
   V11Params p{static_cast<const uint8_t*>(images), static_cast<const uint8_t*>(cb32), debug};
   const int smem = smem_bytes(a.n_levels);
   auto go = [&](auto kernel) -> int {
+    cudaFuncAttributes attr;
+    HV_CUDA_CHECK(cudaFuncGetAttributes(&attr, kernel));
+    if (attr.numRegs < kLaunchRegs) {  // setmaxnreg.inc would wait forever: refuse loudly instead
+      set_error("hv_rq_forward: tcgen05 kernel (generation 11) was built with %d registers/thread, the register hand-over needs %d",
+                attr.numRegs, kLaunchRegs);
+      return HV_ERR_UNSUPPORTED;
+    }
     HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kernel<<<grid, kThreads, smem, stream>>>(a, p);
     HV_CUDA_CHECK(cudaGetLastError());

@@ -1,11 +1,16 @@
 #!/bin/bash
-# A/B timing of the variant libraries under hid-vae_b200/build/variants (encode, 4 Mi and 12,101 rows)
+# A/B timing of the variant libraries under hid-vae_b200/build/variants (encode + train forward, three sizes)
 mkdir -p gpurun_out; rm -f gpurun_out/ab.jsonl gpurun_out/ab.err
 for lib in hid-vae_b200/build/variants/*.so; do
   name=$(basename $lib .so)
-  for rows in 4194304 12101; do
-    HIDVAE_B200_LIB=$PWD/$lib timeout 300 python tools/bench_encode.py --tag $name --rows $rows --shape 32,256,3 --encode-only --reps 20 >> gpurun_out/ab.jsonl 2>> gpurun_out/ab.err
+  if [ -n "$AB_TEST" ]; then HIDVAE_B200_LIB=$PWD/$lib timeout 600 python -m pytest tests/test_gpu_rq.py -m gpu -q -x 2>&1 | tail -2; fi
+  for rows in 4194304 262144 12101; do
+    HIDVAE_B200_LIB=$PWD/$lib timeout 300 python tools/bench_encode.py --tag $name --rows $rows --shape 32,256,3 --reps 20 >> gpurun_out/ab.jsonl 2>> gpurun_out/ab.err
   done
-  case $name in *i) HIDVAE_TC_DEBUG=2 HIDVAE_B200_LIB=$PWD/$lib timeout 300 python tools/bench_encode.py --tag $name-nogather --rows 4194304 --shape 32,256,3 --encode-only --reps 20 >> gpurun_out/ab.jsonl 2>> gpurun_out/ab.err;; esac
 done
-cat gpurun_out/ab.jsonl; tail -5 gpurun_out/ab.err
+python - <<'PY'
+import json
+for l in open('gpurun_out/ab.jsonl'):
+    d=json.loads(l); print(d['tag'],d['rows'],'enc %.4f'%d['encode_ms'],'trainfwd %.4f'%d.get('train_fwd_ms',0))
+PY
+tail -5 gpurun_out/ab.err
