@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
   uint32_t* s_issued = s_free + kAccs;               // [kWGs]   units of the warpgroup the issuer has committed
   uint32_t* s_qtail = s_issued + kWGs;               // requests pushed so far
   uint32_t* s_q = s_qtail + 1;                       // [kQueue] (sequence + 1) << 8 | level << 4 | warpgroup
-  uint32_t* s_tk = s_q + kQueue;                     // [kWGs][2]  first unit number of the warpgroup's level (double-buffered)
-  uint32_t* s_tmem = s_tk + 2 * kWGs;
+  uint32_t* s_tk = s_q + kQueue;                     // [kWGs][2][2]  unit numbers of the warpgroup's level (double-buffered)
+  uint32_t* s_tmem = s_tk + 4 * kWGs;
   uint32_t* s_ts = s_tmem + 1;                       // [192] timestamps of block 0, warpgroup 0 (instrumented builds)
 
   const int warp = threadIdx.x >> 5;
@@ -259,14 +259,31 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
     // =========================================== MMA issuer ===================================================
     if constexpr (kIssuerRegs < kLaunchRegs) ptx::setmaxnreg_dec<kIssuerRegs>();
     if (warp == kIssuerWarp && ptx::elect_one()) {
-      // One request per staged level, both units back to back.  (Requesting unit 1 only when the scan of unit 0 starts,
-      // so that its accumulator is not parked full meanwhile, measured slower: 0.81 vs 0.75 ms at 4 Mi rows.)
+      // One request per staged level.  Unit 0 of a request goes out at once; its unit 1 follows -- after unit 0 of the
+      // NEXT request if one is already queued, so that a waiting tile starts half a level earlier and unit 1's
+      // accumulator is parked full for a shorter time (it cannot be scanned before unit 0 anyway).
       const uint32_t n_req = static_cast<uint32_t>(my_tiles) * static_cast<uint32_t>(n_levels);
       uint32_t unit = 0;  // units issued so far: accumulator = unit % 3, its use number = unit / 3
+      auto issue = [&](uint32_t rwg, uint32_t l, uint32_t u) {
+        s_tk[4 * rwg + 2 * ((s_issued[rwg] >> 1) & 1u) + u] = unit;  // (only this thread writes s_issued: a plain read is exact)
+        const uint32_t acc = unit % kAccs, use = unit / kAccs;
+        ptx::counter_wait(ptx::smem_u32(&s_free[acc]), 4u * use);  // every earlier use of the accumulator is scanned
+        ptx::tc_fence_after_sync();
+        issue_unit(tmem_base + acc * kUnitCols, tmem_base + kAccs * kUnitCols + rwg * D, ones, ptx::smem_u32(s_img + l * kImageBytes),
+                   u * kUnitCols, ptx::smem_u32(&bar_mma_done[acc]));
+        ptx::counter_add_release(ptx::smem_u32(&s_issued[rwg]), 1u);
+        ++unit;
+      };
+      bool have_pending = false;
+      uint32_t pend_wg = 0, pend_l = 0;
       for (uint32_t s = 0; s < n_req; ++s) {
         const uint32_t q_addr = ptx::smem_u32(&s_q[s % kQueue]);
         uint32_t qv = ptx::counter_ld_acquire(q_addr);
         if ((qv >> 8) != s + 1u) {
+          if (have_pending) {  // nothing queued: the deferred unit 1 goes now
+            issue(pend_wg, pend_l, 1u);
+            have_pending = false;
+          }
           const long long t_start = clock64();
           while (((qv = ptx::counter_ld_acquire(q_addr)) >> 8) != s + 1u) {
             if (clock64() - t_start > 4000000000LL) {
@@ -277,18 +294,11 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
         }
         const uint32_t rwg = qv & 0xFu, l = (qv >> 4) & 0xFu;
         if (s < static_cast<uint32_t>(kWGs * n_levels)) ptx::mbar_wait(ptx::smem_u32(&bar_b_full[l]), 0u);  // images are loaded once
-        s_tk[2 * rwg + ((s_issued[rwg] >> 1) & 1u)] = unit;  // (only this thread writes s_issued: a plain read is exact)
-        const uint32_t b_tile = ptx::smem_u32(s_img + l * kImageBytes);
-        const uint32_t ra_tmem = tmem_base + kAccs * kUnitCols + rwg * D;
-#pragma unroll
-        for (uint32_t u = 0; u < 2; ++u, ++unit) {
-          const uint32_t acc = unit % kAccs, use = unit / kAccs;
-          ptx::counter_wait(ptx::smem_u32(&s_free[acc]), 4u * use);  // every earlier use of the accumulator is scanned
-          ptx::tc_fence_after_sync();
-          issue_unit(tmem_base + acc * kUnitCols, ra_tmem, ones, b_tile, u * kUnitCols, ptx::smem_u32(&bar_mma_done[acc]));
-          ptx::counter_add_release(ptx::smem_u32(&s_issued[rwg]), 1u);
-        }
+        issue(rwg, l, 0u);
+        if (have_pending) issue(pend_wg, pend_l, 1u);
+        have_pending = true, pend_wg = rwg, pend_l = l;
       }
+      if (have_pending) issue(pend_wg, pend_l, 1u);
     }
     __syncwarp();
   } else {
@@ -366,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
       for (uint32_t u = 0; u < 2; ++u) {
         if (lane == 0) ptx::counter_wait(ptx::smem_u32(&s_issued[wg]), 2u * lvl + u + 1u);  // issued: the parity is now exact
         __syncwarp();
-        const uint32_t tk = *reinterpret_cast<volatile uint32_t*>(&s_tk[2 * wg + (lvl & 1)]) + u, acc = tk % kAccs, use = tk / kAccs;
+        const uint32_t tk = *reinterpret_cast<volatile uint32_t*>(&s_tk[4 * wg + 2 * (lvl & 1) + u]), acc = tk % kAccs, use = tk / kAccs;
         ptx::mbar_wait(ptx::smem_u32(&bar_mma_done[acc]), use & 1u);
         ptx::tc_fence_after_sync();
         if (u == 0) stamp(5);
@@ -388,11 +398,11 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
       if (tail) {
         // ---- the chosen fp32 code row from shared memory (chunk c of code k sits at chunk c ^ (k & 7)) ----
         float e[D];
-        const uint32_t row_addr = ptx::smem_u32(s_cb + l * kCbBytes) + k_sel * (D * 4);
-        const uint32_t sw = k_sel & 7u;
+        // (rows are 128-byte aligned: (c ^ sw) << 4 == (c << 4) ^ (sw << 4), one LOP3 with an immediate per chunk)
+        const uint32_t row_sw = (ptx::smem_u32(s_cb + l * kCbBytes) + k_sel * (D * 4)) | ((k_sel & 7u) << 4);
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) {
-          const float4 v = ptx::lds128(row_addr + ((c ^ sw) << 4));
+          const float4 v = ptx::lds128(row_sw ^ (c << 4));
           e[4 * c] = v.x, e[4 * c + 1] = v.y, e[4 * c + 2] = v.z, e[4 * c + 3] = v.w;
         }
         if (tail_last) {  // something besides ids is wanted: value / loss / outputs (modules/quantize.py:131-148)

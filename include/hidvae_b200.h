@@ -95,8 +95,10 @@ int hv_rq_forward(const float* x, int64_t n, int d, const float* codebooks, int 
 
 /*
  * Writes the tensor-core operand image of the effective codebooks (bf16 hi/lo split in the UMMA core-matrix
- * layout plus the -|c|^2/2 terms) into `workspace` (>= hv_workspace_bytes(HV_OP_RQ_FORWARD, ...)).  hv_rq_forward
- * does this itself for HV_ALGO_TCGEN05 / AUTO; call it once and pass HV_ALGO_TCGEN05_PREPACKED to reuse the image.
+ * layout plus the -|c|^2/2 terms) into `workspace` (>= hv_workspace_bytes(HV_OP_RQ_FORWARD, ...)) and, for shapes
+ * whose codebooks stay resident in shared memory (D = 32, K <= 256, L <= 3), a chunk-swizzled fp32 copy of the
+ * codebooks behind it (the kernel gathers the chosen code rows from that copy).  hv_rq_forward does this itself for
+ * HV_ALGO_TCGEN05 / AUTO; call it once and pass HV_ALGO_TCGEN05_PREPACKED to reuse the image.
  */
 int hv_rq_pack_codebooks(const float* codebooks, int n_levels, int k, int d, void* workspace, size_t workspace_bytes,
                          void* stream);

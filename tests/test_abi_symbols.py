@@ -53,7 +53,9 @@ def test_version_and_error_channel(lib_mod):
 
 def test_workspace_sizes(lib_mod):
     ws = lib_mod.lib.hv_workspace_bytes
-    assert ws(lib_mod.HV_OP_RQ_FORWARD, 0, 32, 256, 3) == 3 * 256 * (4 * 32 + 32)      # config 1/2/3/5
+    # config 1/2/3/5: operand images + the swizzled fp32 copy the resident-codebook kernel gathers from
+    assert ws(lib_mod.HV_OP_RQ_FORWARD, 0, 32, 256, 3) == 3 * 256 * (4 * 32 + 32) + 3 * 256 * 32 * 4
+    assert ws(lib_mod.HV_OP_RQ_FORWARD, 0, 32, 512, 3) == 3 * 512 * (4 * 32 + 32)      # two images per level: images only
     assert ws(lib_mod.HV_OP_RQ_FORWARD, 0, 64, 4096, 4) == 4 * 4096 * (4 * 64 + 32)    # config 4
     assert ws(lib_mod.HV_OP_RQ_FORWARD, 0, 20, 256, 3) == 0                            # no tcgen05 instantiation
     assert ws(lib_mod.HV_OP_RQ_BACKWARD, 0, 32, 256, 3) == 0
