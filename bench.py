@@ -323,11 +323,11 @@ def run_native(args):
     b_fwd = n * (4 * d + 4 * d * L + 8 * L + 4)
     b_bwd = n * (4 * d + 8 * L + 4 * d * L + 4 + 4 * d) + 4 * L * k * d
     kernels = [
-        dict(kernel="rq_fwd_tc_kernel<32,rot> (train forward)", ms=t_fwd, bound="tensor", achieved=flops / (t_fwd * 1e-3) / 1e12,
+        dict(kernel="rq_fwd_tc_v11_kernel<rot> (train forward)", ms=t_fwd, bound="tensor", achieved=flops / (t_fwd * 1e-3) / 1e12,
              peak=pk["tensor"], unit="TFLOP/s", hbm_gbs=b_fwd / (t_fwd * 1e-3) / 1e9),
         dict(kernel="rq_bwd_kernel<32,rot> (backward)", ms=t_bwd, bound="hbm", achieved=b_bwd / (t_bwd * 1e-3) / 1e9, peak=pk["hbm"],
              unit="GB/s"),
-        dict(kernel="rq_fwd_tc_kernel<32> (eval encode)", ms=t_enc, bound="tensor", achieved=flops / (t_enc * 1e-3) / 1e12,
+        dict(kernel="rq_fwd_tc_v11_kernel (eval encode)", ms=t_enc, bound="tensor", achieved=flops / (t_enc * 1e-3) / 1e12,
              peak=pk["tensor"], unit="TFLOP/s", hbm_gbs=b_enc / (t_enc * 1e-3) / 1e9),
     ]
     traffic = ncu_traffic()
