@@ -174,7 +174,8 @@ struct V11Params {
   int debug;
 };
 
-template <bool ROT>
+// OUT = false: ids only (bulk assignment / eval encode without outputs) -- the value / loss / output code is compiled out
+template <bool ROT, bool OUT>
 __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a, V11Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // [ones | barriers + counters | operand images (L) | fp32 codebooks (L)]
@@ -251,9 +252,9 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
   const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
   const int my_tiles = static_cast<int>((n_row_tiles - 1 - blockIdx.x) / gridDim.x + 1);  // grid <= n_row_tiles
   auto tile_row0 = [&](int i) -> int64_t { return (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x) * kTileRows; };
-  const bool want_loss = a.loss != nullptr || a.level_loss != nullptr;
+  const bool want_loss = OUT && (a.loss != nullptr || a.level_loss != nullptr);
   // the last level's code row is only needed when something other than ids is asked for
-  const bool tail_last = a.emb_out != nullptr || want_loss || a.final_residual != nullptr;
+  const bool tail_last = OUT && (a.emb_out != nullptr || want_loss || a.final_residual != nullptr);
 
   if (warp >= kIssuerWarp) {
     // =========================================== MMA issuer ===================================================
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
       const bool last = l + 1 == n_levels;
       const bool tail = !last || tail_last;
       stamp(2);
-      if (a.residuals != nullptr && valid) store_row<D>(a.residuals + (static_cast<int64_t>(l) * a.n + grow) * D, r);
+      if (OUT && a.residuals != nullptr && valid) store_row<D>(a.residuals + (static_cast<int64_t>(l) * a.n + grow) * D, r);
       // ---- the residual's bf16 hi | lo halves -> the warpgroup's A columns in tensor memory ----
       {
         uint32_t hi[16], lo[16];
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
           const float4 v = ptx::lds128(row_sw ^ (c << 4));
           e[4 * c] = v.x, e[4 * c + 1] = v.y, e[4 * c + 2] = v.z, e[4 * c + 3] = v.w;
         }
-        if (tail_last) {  // something besides ids is wanted: value / loss / outputs (modules/quantize.py:131-148)
+        if (OUT && tail_last) {  // something besides ids is wanted: value / loss / outputs (modules/quantize.py:131-148)
           float* o_out = (valid && a.emb_out != nullptr) ? a.emb_out + (static_cast<int64_t>(l) * a.n + grow) * D : nullptr;
           const float ll = rq_level_tail<D, ROT>(r, e, a.beta, o_out);
           loss += ll;
@@ -483,7 +484,9 @@ int launch_rq_fwd_tc_v11(const RqFwdArgs& a, bool rot, const void* images, const
     HV_CUDA_CHECK(cudaGetLastError());
     return HV_OK;
   };
-  return rot ? go(rq_fwd_tc_v11_kernel<true>) : go(rq_fwd_tc_v11_kernel<false>);
+  const bool out = a.emb_out != nullptr || a.loss != nullptr || a.level_loss != nullptr || a.final_residual != nullptr || a.residuals != nullptr;
+  if (!out) return go(rq_fwd_tc_v11_kernel<false, false>);
+  return rot ? go(rq_fwd_tc_v11_kernel<true, true>) : go(rq_fwd_tc_v11_kernel<false, true>);
 }
 
 }  // namespace hv
