@@ -266,19 +266,35 @@ def run_native(args):
     cb_param = cbs.clone().requires_grad_(True)
 
     side = torch.cuda.Stream()
+    feed = torch.cuda.Stream()
+    # Double-buffered input feed (what a DataLoader with pinned-memory prefetch does): the H2D copy of step i+1's inputs
+    # runs on its own stream beside step i's kernels.  EVERY step still issues one H2D of its inputs' size and one D2H of
+    # its results inside its timed region; `serial_ms_per_step` below is the same step with the copy in front of the kernels.
+    x_dev = [torch.empty((n, d), device="cuda").requires_grad_(True) for _ in range(2)]
+    tg_dev = [torch.empty((n, d), device="cuda") for _ in range(2)]
 
-    def e2e_step():
+    def e2e_step(j=0, prefetch=False):
         main = torch.cuda.current_stream()
-        xd = x_h.to("cuda", non_blocking=True).requires_grad_(True)
+        cur, nxt = j & 1, (j & 1) ^ 1
+        if prefetch:
+            feed.wait_stream(main)                                          # (the previous step has released buffer `nxt`)
+            with torch.cuda.stream(feed), torch.no_grad():
+                x_dev[nxt].copy_(x_h, non_blocking=True)
+                tg_dev[nxt].copy_(tgt_h, non_blocking=True)
+        else:
+            with torch.no_grad():
+                x_dev[cur].copy_(x_h, non_blocking=True)
+                tg_dev[cur].copy_(tgt_h, non_blocking=True)
+        xd, tg = x_dev[cur], tg_dev[cur]
         packed = ops.pack_codebooks(cb_param.detach())
         side.wait_stream(main)
         with torch.cuda.stream(side):                                       # eval encode + its D2H beside the training step
             enc = ops.rq_encode(xd.detach(), cb_param.detach(), packed=packed)
             enc_h.copy_(enc, non_blocking=True)
-        tg = tgt_h.to("cuda", non_blocking=True)
         emb, _res, ids, loss, _ll = ops.RqFunction.apply(xd, cb_param, MODE_ROT, True, beta, "auto")
         total = ((emb.sum(0) - tg) ** 2).sum(-1).mean() + loss.mean()      # h_rqvae.py:607-640 shaped consumer
         cb_param.grad = None
+        xd.grad = None
         total.backward()
         if comm is not None:
             comm.allreduce_async(cb_param.grad)
@@ -287,22 +303,46 @@ def run_native(args):
         if comm is not None:
             comm.wait()
         main.wait_stream(side)
-        for t_ in (xd, packed, enc):
+        if prefetch:
+            main.wait_stream(feed)
+        for t_ in (packed, enc):
             t_.record_stream(side)
+
+    class Alternating:
+        """Steps 0, 1, 0, 1, ... (one captured graph per input buffer)."""
+
+        def __init__(self, even, odd):
+            self.fns, self.j = (even, odd), 0
+
+        def __call__(self):
+            self.fns[self.j & 1]()
+            self.j += 1
 
     if world > 1:
         dist.barrier()
     # the public API is graph-capturable (no host-side data-dependent branches, every call on the current stream):
     # a training loop with static shapes replays ONE graph per step -- pinned-host H2D, kernels, D2H included
-    e2e_run, e2e_graphed = e2e_step, False
+    with torch.no_grad():
+        x_dev[0].copy_(x_h)
+        tg_dev[0].copy_(tgt_h)
+    e2e_run, e2e_graphed = Alternating(lambda: e2e_step(0, True), lambda: e2e_step(1, True)), False
+    e2e_serial = lambda: e2e_step(0, False)
     if not args.no_graph:
         try:
-            e2e_run, e2e_graphed = GraphedStep(e2e_step), True
+            e2e_run = Alternating(GraphedStep(lambda: e2e_step(0, True)), GraphedStep(lambda: e2e_step(1, True)))
+            e2e_serial = GraphedStep(lambda: e2e_step(0, False))
+            e2e_graphed = True
         except Exception as e:
             print(f"[bench] e2e CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager calls", file=sys.stderr)
             torch.cuda.synchronize()
+    ser_steps = min(args.steps, 100)
+    e2e_serial_ms = time_region(e2e_serial, ser_steps, 3, flush) / ser_steps
+    with torch.no_grad():                                                   # buffer 0 holds the first step's inputs
+        x_dev[0].copy_(x_h)
+        tg_dev[0].copy_(tgt_h)
+    torch.cuda.synchronize()
     e2e_ms = time_region(e2e_run, args.steps, args.warmup, flush)
-    e2e_eager_ms = time_region(e2e_step, min(args.steps, 100), 3, flush) / min(args.steps, 100) if e2e_graphed else None
+    e2e_eager_ms = time_region(lambda: e2e_step(0, False), min(args.steps, 100), 3, flush) / min(args.steps, 100) if e2e_graphed else None
     te = torch.tensor([e2e_ms], device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -354,7 +394,9 @@ def run_native(args):
                     config=dict(WORKLOAD, parallelism=f"dp{world}", items_per_step_per_gpu=n, cuda_graph=graphed,
                                 eager_ms_per_step=eager_ms),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             ms_per_step=e2e_ms / args.steps, cuda_graph=e2e_graphed, eager_ms_per_step=e2e_eager_ms),
+                             ms_per_step=e2e_ms / args.steps, cuda_graph=e2e_graphed, eager_ms_per_step=e2e_eager_ms,
+                             input_feed="double-buffered: step i+1's pinned-host H2D on a copy stream beside step i's kernels; one H2D + one D2H per timed step",
+                             serial_ms_per_step=e2e_serial_ms),
                     gpu_launches=NativeStep.LAUNCHES_PER_STEP * args.steps, roofline=roofline, cpu_baseline=cpu,
                     clocks=clocks, impl="native")
         if sweep is not None:
