@@ -321,3 +321,58 @@ def test_full_size_properties(ops, shape):
     rows = torch.arange(0, n, n // 4096)[:4096]
     match = check_ids(ids[rows.cuda()], x[rows.cuda()].cpu(), cbs.cpu(), O.MODE_STE, 0.25, False)
     assert match.float().mean() > 0.995
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the resident-codebook kernel (D = 32, K <= 256, L <= 3: rows owned by threads, A operand in tensor memory, issuer warp,
+# three shared accumulators): shapes around its unit / padding boundaries and long accumulator rings
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [8, 100, 128, 129, 200, 256])
+@pytest.mark.parametrize("L", [1, 2, 3])
+def test_resident_kernel_codebook_sizes(ops, k, L):
+    """K below / at / above one 128-code unit (padded codes can never win, an all-padding unit 1 must lose to unit 0)."""
+    n, d = 1000 + 37 * L + k, 32
+    x = unit_rows(n, d, seed=k + L)
+    cbs = make_codebooks(L, k, d, seed=3 * k + L)
+    out = _run_forward(ops, x, cbs, O.MODE_ROTATION_TRICK, True, 0.4, "tcgen05")
+    assert int(out.ids.max()) < k and int(out.ids.min()) >= 0
+    match = check_ids(out.ids, x, cbs, O.MODE_ROTATION_TRICK, 0.4, True)
+    assert match.float().mean() > 0.995
+    ref = oracle_levels(x, cbs, O.MODE_ROTATION_TRICK, 0.4, True)
+    _compare_values(out, ref, match & (out.ids.cpu() == ref.sem_ids).all(dim=1))
+
+
+def test_resident_kernel_ties_across_units(ops):
+    """Duplicate code rows inside a 16-column chunk, in another chunk of the same column class, and in the other unit:
+    the lowest index wins (the unit-0 candidate keeps ties against unit 1)."""
+    d, k = 32, 256
+    gen = torch.Generator().manual_seed(11)
+    for first, dups in [(5, [6]), (5, [21]), (5, [133]), (100, [116, 228]), (127, [128]), (0, [255]), (130, [131, 146, 250])]:
+        cb = make_codebooks(3, k, d, seed=9)
+        for j in dups:
+            cb[0, j] = cb[0, first]
+        x = cb[0, first].repeat(300, 1) + 1e-3 * torch.randn(300, d, generator=gen)
+        ids = ops.rq_encode(_dev(x), _dev(cb), algo="tcgen05").cpu()
+        assert (ids[:, 0] == first).all(), (first, dups, ids[:, 0].unique())
+
+
+@pytest.mark.parametrize("training", [0, 1])
+def test_resident_kernel_many_tiles_per_warpgroup(ops, training):
+    """~13 row tiles per CTA: the request queue, the unit counter and the three accumulators wrap many times; every
+    row must agree with the exact fp32 CUDA-core kernel (ids up to documented near-ties, values where ids agree)."""
+    n, d, k, L = 148 * 128 * 13 + 77, 32, 256, 3
+    x = _dev(unit_rows(n, d, seed=77))
+    cbs = _dev(make_codebooks(L, k, d, seed=78))
+    kw = dict(want_emb=True, want_loss=True) if training else {}
+    a = ops.rq_forward(x, cbs, O.MODE_ROTATION_TRICK, bool(training), 0.4, algo="tcgen05", **kw)
+    b = ops.rq_forward(x, cbs, O.MODE_ROTATION_TRICK, bool(training), 0.4, algo="simt", **kw)
+    same = (a.ids == b.ids).all(dim=1)
+    assert float(same.float().mean()) > 0.999
+    # reconstruction identity on every row, whatever the ids: x - sum_l C_l[id_l] (eval) is what the next level saw
+    if training:
+        torch.testing.assert_close(a.emb_out[:, same], b.emb_out[:, same], **VAL)
+        torch.testing.assert_close(a.loss[same], b.loss[same], **VAL)
+    # rows that differ must be near-ties: check them against the oracle on a sample
+    bad = torch.nonzero(~same).view(-1)[:512].cpu()
+    if bad.numel():
+        check_ids(a.ids[bad.cuda()], x[bad.cuda()].cpu(), cbs.cpu(), O.MODE_ROTATION_TRICK, 0.4, bool(training))
