@@ -112,23 +112,28 @@ __global__ void __launch_bounds__(kBwdThreads, NL > 0 ? HV_BWD_MINB : 1) rq_bwd_
         E[l] = e;
         float4 o = e;
         if (rot) {
+          // modules/quantize.py:34-45 with u = r ir, q = e ie, s = u + q.  r.u = rr ir and r.s = rr ir + re ie follow from
+          // the row sums r.r, e.e, r.e (4 shuffle reductions instead of 5); |s|^2 stays the literal sum: 1/|s| scales the
+          // Jacobian term, and its rounding must stay at the reference's level (a product form cost 3e-7 of |g| there)
           const float rr = group_sum<LPR>(dot4(r, r));
           const float ee = group_sum<LPR>(dot4(e, e));
+          const float re = group_sum<LPR>(dot4(r, e));
           const float ir = 1.0f / (sqrtf(rr) + 1e-8f);
           const float ie = 1.0f / (sqrtf(ee) + 1e-8f);
-          const float4 u = make_float4(r.x * ir, r.y * ir, r.z * ir, r.w * ir);
-          const float4 q = make_float4(e.x * ie, e.y * ie, e.z * ie, e.w * ie);
-          const float4 s = make_float4(u.x + q.x, u.y + q.y, u.z + q.z, u.w + q.w);
-          const float ss = group_sum<LPR>(dot4(s, s));
-          const float ru = group_sum<LPR>(dot4(r, u));
-          const float rs = group_sum<LPR>(dot4(r, s));
+          const float ru = rr * ir;
+          const float rq = re * ie;
+          const float4 sv = make_float4(fmaf(r.x, ir, e.x * ie), fmaf(r.y, ir, e.y * ie), fmaf(r.z, ir, e.z * ie), fmaf(r.w, ir, e.w * ie));
+          const float ss = group_sum<LPR>(dot4(sv, sv));
+          const float rs = ru + rq;
           const float is = 1.0f / fmaxf(sqrtf(ss), 1e-6f);
           inv_r[l] = ir, inv_e[l] = ie, inv_s[l] = is;
-          const float rw2 = 2.0f * (rs * is), ru2 = 2.0f * ru;
-          o.x = r.x - rw2 * (s.x * is) + ru2 * q.x;
-          o.y = r.y - rw2 * (s.y * is) + ru2 * q.y;
-          o.z = r.z - rw2 * (s.z * is) + ru2 * q.z;
-          o.w = r.w - rw2 * (s.w * is) + ru2 * q.w;
+          // o = r - 2 (r.w) w + 2 (r.u) q  with w = (u + q) is:   o = r (1 - a ir) + e (b - a) ie,  a = 2 rs is^2, b = 2 ru
+          const float a2 = 2.0f * rs * is * is, b2 = 2.0f * ru;
+          const float cr = 1.0f - a2 * ir, ce = (b2 - a2) * ie;
+          o.x = fmaf(cr, r.x, ce * e.x);
+          o.y = fmaf(cr, r.y, ce * e.y);
+          o.z = fmaf(cr, r.z, ce * e.z);
+          o.w = fmaf(cr, r.w, ce * e.w);
         }
         r = make_float4(r.x - o.x, r.y - o.y, r.z - o.z, r.w - o.w);
       }
