@@ -168,37 +168,10 @@ __device__ __forceinline__ void issue_unit(uint32_t acc, uint32_t a_tmem, uint32
   ptx::umma_commit(bar_done);
 }
 
-// A thread moves its whole 128-byte row: 256-bit accesses (LDG/STG.E.ENL2.256) cover a full 32-byte sector per lane and
-// halve the load/store-pipe instructions of the thread-per-row pattern; they need 32-byte aligned rows (`wide`).
-__device__ __forceinline__ void load_row_wide(float (&dst)[D], const float* __restrict__ src, bool wide) {
-  if (wide) {
-#pragma unroll
-    for (int i = 0; i < D; i += 8)
-      asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                   : "=f"(dst[i]), "=f"(dst[i + 1]), "=f"(dst[i + 2]), "=f"(dst[i + 3]), "=f"(dst[i + 4]), "=f"(dst[i + 5]),
-                     "=f"(dst[i + 6]), "=f"(dst[i + 7])
-                   : "l"(src + i));
-  } else {
-    load_row<D>(dst, src);
-  }
-}
-__device__ __forceinline__ void store_row_wide(float* __restrict__ dst, const float (&src)[D], bool wide) {
-  if (wide) {
-#pragma unroll
-    for (int i = 0; i < D; i += 8)
-      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + i), "f"(src[i]), "f"(src[i + 1]),
-                   "f"(src[i + 2]), "f"(src[i + 3]), "f"(src[i + 4]), "f"(src[i + 5]), "f"(src[i + 6]), "f"(src[i + 7])
-                   : "memory");
-  } else {
-    store_row<D>(dst, src);
-  }
-}
-
 struct V11Params {
   const uint8_t* images;  // [L] packed bf16 images
   const uint8_t* cb32;    // [L] swizzled fp32 codebooks
   int debug;
-  int wide;  // x and every output are 32-byte aligned: 256-bit row accesses
 };
 
 // OUT = false: ids only (bulk assignment / eval encode without outputs) -- the value / loss / output code is compiled out
@@ -335,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
   auto load_x = [&](int i) {  // the thread's row of this CTA's i-th tile (rows beyond n read as zero)
     const int64_t grow = tile_row0(i) + t;
     if (grow < a.n) {
-      load_row_wide(r, a.x + grow * D, p.wide != 0);
+      load_row<D>(r, a.x + grow * D);
     } else {
 #pragma unroll
       for (int d = 0; d < D; ++d) r[d] = 0.f;
@@ -363,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
       const bool last = l + 1 == n_levels;
       const bool tail = !last || tail_last;
       stamp(2);
-      if (OUT && a.residuals != nullptr && valid) store_row_wide(a.residuals + (static_cast<int64_t>(l) * a.n + grow) * D, r, p.wide != 0);
+      if (OUT && a.residuals != nullptr && valid) store_row<D>(a.residuals + (static_cast<int64_t>(l) * a.n + grow) * D, r);
       // ---- the residual's bf16 hi | lo halves -> the warpgroup's A columns in tensor memory ----
       {
         uint32_t hi[16], lo[16];
@@ -434,14 +407,13 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
           e[4 * c] = v.x, e[4 * c + 1] = v.y, e[4 * c + 2] = v.z, e[4 * c + 3] = v.w;
         }
         if (OUT && tail_last) {  // something besides ids is wanted: value / loss / outputs (modules/quantize.py:131-148)
-          float o[D];
-          const float ll = rq_level_tail_o<D, ROT>(r, e, a.beta, o);
-          if (valid && a.emb_out != nullptr) store_row_wide(a.emb_out + (static_cast<int64_t>(l) * a.n + grow) * D, o, p.wide != 0);
+          float* o_out = (valid && a.emb_out != nullptr) ? a.emb_out + (static_cast<int64_t>(l) * a.n + grow) * D : nullptr;
+          const float ll = rq_level_tail<D, ROT>(r, e, a.beta, o_out);
           loss += ll;
           if (valid) {
             if (a.level_loss != nullptr) a.level_loss[static_cast<int64_t>(l) * a.n + grow] = ll;
             if (last && a.loss != nullptr) a.loss[grow] = loss;
-            if (last && a.final_residual != nullptr) store_row_wide(a.final_residual + grow * D, r, p.wide != 0);
+            if (last && a.final_residual != nullptr) store_row<D>(a.final_residual + grow * D, r);
           }
         } else {
 #pragma unroll
@@ -497,9 +469,7 @@ int launch_rq_fwd_tc_v11(const RqFwdArgs& a, bool rot, const void* images, const
     const char* e = getenv("HIDVAE_TC_DEBUG");
     return e != nullptr ? atoi(e) : 0;
   }();
-  auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
-  const int wide = al32(a.x) && al32(a.emb_out) && al32(a.residuals) && al32(a.final_residual) ? 1 : 0;
-  V11Params p{static_cast<const uint8_t*>(images), static_cast<const uint8_t*>(cb32), debug, wide};
+  V11Params p{static_cast<const uint8_t*>(images), static_cast<const uint8_t*>(cb32), debug};
   const int smem = smem_bytes(a.n_levels);
   auto go = [&](auto kernel) -> int {
     cudaFuncAttributes attr;
