@@ -156,22 +156,39 @@ class NativeStep:
 
 
 class GradComm:
-    """Codebook-gradient all-reduce on a side stream so it overlaps the eval encode."""
+    """Codebook-gradient all-reduce.  Default: the one-kernel exchange over NVLink peer memory
+    (hidvae_b200.dist.PeerAllReduce -> hv_peer_allreduce), in place on the current stream.  HIDVAE_BENCH_NCCL=1 (or a
+    node without symmetric-memory support) uses NCCL on a side stream so that it overlaps the eval encode."""
 
-    def __init__(self):
+    def __init__(self, numel, device):
         import torch.distributed as dist
         self.dist = dist
         self.stream = torch.cuda.Stream()
-        self.work = None
+        self.peer = None
+        if os.environ.get("HIDVAE_BENCH_NCCL", "0") != "1":
+            try:
+                from hidvae_b200.dist import PeerAllReduce
+                self.peer = PeerAllReduce(numel, device)
+            except Exception as e:  # noqa: BLE001
+                print(f"[bench] peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+        flag = torch.tensor([1 if self.peer is not None else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank must take the same path
+        if int(flag.item()) == 0:
+            self.peer = None
+        self.kind = "peer-memory one-shot kernel (hv_peer_allreduce)" if self.peer is not None else "nccl"
 
     def allreduce_async(self, t):
+        if self.peer is not None:
+            self.peer(t.view(-1))
+            return
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             self.dist.all_reduce(t)
         t.record_stream(self.stream)
 
     def wait(self):
-        torch.cuda.current_stream().wait_stream(self.stream)
+        if self.peer is None:
+            torch.cuda.current_stream().wait_stream(self.stream)
 
 
 class GraphedStep:
@@ -229,7 +246,7 @@ def run_native(args):
     x, cbs, g_emb, g_loss = synth(n, d, k, L, seed=rank, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     step = NativeStep(ops, x, cbs, g_emb, g_loss, beta)
-    comm = GradComm() if world > 1 else None
+    comm = GradComm(cbs.numel(), cbs.device) if world > 1 else None
     pk = peaks()
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -392,12 +409,12 @@ def run_native(args):
                     ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32 (argmin scores: bf16x3 split on tcgen05, fp32 accumulate)", data="synthetic",
                     config=dict(WORKLOAD, parallelism=f"dp{world}", items_per_step_per_gpu=n, cuda_graph=graphed,
-                                eager_ms_per_step=eager_ms),
+                                eager_ms_per_step=eager_ms, grad_allreduce=(comm.kind if comm is not None else None)),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=e2e_ms / args.steps, cuda_graph=e2e_graphed, eager_ms_per_step=e2e_eager_ms,
                              input_feed="double-buffered: step i+1's pinned-host H2D on a copy stream beside step i's kernels; one H2D + one D2H per timed step",
                              serial_ms_per_step=e2e_serial_ms),
-                    gpu_launches=NativeStep.LAUNCHES_PER_STEP * args.steps, roofline=roofline, cpu_baseline=cpu,
+                    gpu_launches=(NativeStep.LAUNCHES_PER_STEP + (1 if comm is not None and comm.peer is not None else 0)) * args.steps, roofline=roofline, cpu_baseline=cpu,
                     clocks=clocks, impl="native")
         if sweep is not None:
             line["sweep"] = sweep

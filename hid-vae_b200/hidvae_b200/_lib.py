@@ -48,6 +48,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p]),
     "hv_uniq_backward": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_float, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hv_peer_allreduce_chunks": (c_int, [c_int64]),
+    "hv_peer_allreduce": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
 

@@ -81,3 +81,41 @@ def shard_range(n: int, rank: int, world: int) -> tuple:
     """Contiguous [lo, hi) of `n` items owned by `rank` (bulk semantic-ID assignment shards by items)."""
     per = (n + world - 1) // world
     return min(rank * per, n), min((rank + 1) * per, n)
+
+
+class PeerAllReduce:
+    """In-place sum of a small fp32 tensor over all ranks as ONE kernel over NVLink / NVSwitch peer memory
+    (`hv_peer_allreduce`, csrc/peer_allreduce.cu): every rank pushes its contribution into an inbox on every peer and sums
+    the inboxes in rank order, so all ranks end with bit-identical results.  For the latency-bound exchanges of the
+    quantiser (98 KB of codebook gradient per step); large buffers belong to NCCL (`FlatGradAllReduce`).
+    The inboxes and flags are a symmetric allocation (torch.distributed._symmetric_memory: CUDA peer mappings between the
+    processes of one node).  No fallback: a node without peer access fails in the constructor."""
+
+    def __init__(self, numel: int, device, group=None) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from hidvae_b200._lib import lib
+        if numel % 4:
+            raise ValueError("PeerAllReduce: numel must be a multiple of 4 (rows are moved as 16-byte vectors)")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.n = dist.get_world_size(self.group), dist.get_rank(self.group), numel
+        n_chunks = int(lib.hv_peer_allreduce_chunks(numel))
+        name = self.group.group_name
+        self.inbox = symm_mem.empty(2 * self.world * numel, dtype=torch.float32, device=device)
+        self.flags = symm_mem.empty(2 * self.world * n_chunks, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        h_inbox, h_flags = symm_mem.rendezvous(self.inbox, name), symm_mem.rendezvous(self.flags, name)
+        self.inbox_ptrs = torch.tensor([int(p) for p in h_inbox.buffer_ptrs], dtype=torch.int64, device=device)
+        self.flag_ptrs = torch.tensor([int(p) for p in h_flags.buffer_ptrs], dtype=torch.int64, device=device)
+        self.seq = torch.zeros(n_chunks, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)  # every rank's flags are zero before anybody pushes
+
+    def __call__(self, t: torch.Tensor) -> torch.Tensor:
+        from hidvae_b200._lib import check, lib
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != self.n:
+            raise ValueError(f"PeerAllReduce: expected a contiguous fp32 tensor of {self.n} elements")
+        with torch.cuda.device(t.device):
+            check(lib.hv_peer_allreduce(t.data_ptr(), t.data_ptr(), self.n, self.inbox_ptrs.data_ptr(), self.flag_ptrs.data_ptr(),
+                                        self.seq.data_ptr(), self.rank, self.world, torch.cuda.current_stream(t.device).cuda_stream))
+        return t

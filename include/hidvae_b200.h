@@ -153,6 +153,20 @@ int hv_uniq_backward(const int64_t* ids, int64_t rows, int64_t width, int64_t ro
                      const float* feats, int d, float margin, float weight, const double* stats,
                      const float* g_out, float* g_feats, void* stream);
 
+/*
+ * Data-parallel exchange of a small fp32 buffer (the codebook gradient, train_hidvae.py's DDP all-reduce) as ONE kernel
+ * over NVLink / NVSwitch peer memory: every rank pushes its contribution into an inbox slot on every peer, flags it,
+ * waits for its peers' flags and sums the slots in rank order (bit-identical results on every rank).
+ *   n           floats, multiple of 4
+ *   inbox_ptrs  device array [world] of the ranks' inbox bases as mapped in THIS process (symmetric allocation of
+ *               2 * world * n floats per rank); flag_ptrs likewise for 2 * world * hv_peer_allreduce_chunks(n) uint32 flags
+ *               (zero before the first call); seq: hv_peer_allreduce_chunks(n) private uint32 counters (zero before the
+ *               first call).  Every rank must make the same sequence of calls.  CUDA-graph capturable.
+ */
+int hv_peer_allreduce_chunks(int64_t n);
+int hv_peer_allreduce(const float* src, float* dst, int64_t n, const uint64_t* inbox_ptrs, const uint64_t* flag_ptrs,
+                      uint32_t* seq, int rank, int world, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,3 +123,23 @@ def test_uniqueness_degenerate_batches(ops):
     assert float(ops.uniqueness_loss(torch.zeros(1, 3, dtype=torch.int64).cuda(), feats, 0.0, 1.0)) == 0.0
     ids = torch.zeros(0, 3, dtype=torch.int64).cuda()
     assert float(ops.uniqueness_loss(ids, torch.zeros(0, 32).cuda(), 0.0, 1.0)) == 0.0
+
+
+def test_peer_allreduce_two_gpus():
+    """hv_peer_allreduce (one kernel over NVLink peer memory) against NCCL on the codebook-gradient size: values,
+    bit-identical results on every rank, CUDA-graph replay.  Needs two GPUs on the box (tools/check_peer_allreduce.py)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29547", os.path.join(root, "tools", "check_peer_allreduce.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["ok"] is True
