@@ -19,7 +19,7 @@ from modules.tokenizer.h_semids import HSemanticIdTokenizer  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--items", type=int, default=1 << 21)
-ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--reps", type=int, default=5)  # (the tokenizer option `encoder_tf32` makes the same choice per call)
 args = ap.parse_args()
 torch.cuda.set_device(0)
 torch.manual_seed(0)
