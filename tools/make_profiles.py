@@ -38,7 +38,9 @@ launches = rows[2:]
 small = {"train_forward": None, "backward": None, "eval_encode": None}
 big = dict(small)
 for r in launches:  # first three = the C2 step, the long ones = the 1 Mi-row launches
-    kind = "backward" if "rq_bwd_kernel" in r[name] else ("train_forward" if ("<1>" in r[name] or "(bool)1" in r[name]) else ("eval_encode" if "rq_fwd_tc" in r[name] else None))
+    nm = r[name]
+    # rq_fwd_tc_v11_kernel<ROT, OUT>: OUT = 1 is the training forward (outputs), <0, 0> the ids-only encode
+    kind = "backward" if "rq_bwd_kernel" in nm else (None if "rq_fwd_tc" not in nm else ("eval_encode" if ("<0, 0>" in nm or "(bool)0, (bool)0" in nm) else "train_forward"))
     if kind is None: continue
     tgt = big if float(r[ms]) > 100 else small
     if tgt[kind] is None: tgt[kind] = total(r)
