@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -46,6 +47,33 @@ int device_props(DeviceProps* out) {
     g_props_known[dev] = true;
   }
   *out = g_props[dev];
+  return HV_OK;
+}
+
+int prepare_kernel_impl(const void* kernel, int min_regs, int smem_bytes) {
+  struct Entry { const void* kernel; int dev; int smem; };
+  static std::mutex mu;
+  static std::vector<Entry> done;
+  int dev = -1;
+  HV_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  for (Entry& e : done)
+    if (e.kernel == kernel && e.dev == dev) {
+      if (e.smem >= smem_bytes) return HV_OK;
+      HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      e.smem = smem_bytes;
+      return HV_OK;
+    }
+  if (min_regs > 0) {
+    cudaFuncAttributes attr;
+    HV_CUDA_CHECK(cudaFuncGetAttributes(&attr, kernel));
+    if (attr.numRegs < min_regs) {
+      set_error("kernel was built with %d registers/thread, its register hand-over needs %d", attr.numRegs, min_regs);
+      return HV_ERR_UNSUPPORTED;
+    }
+  }
+  HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  done.push_back({kernel, dev, smem_bytes});
   return HV_OK;
 }
 

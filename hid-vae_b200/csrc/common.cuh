@@ -31,6 +31,15 @@ struct DeviceProps {
 // cached per device; returns non-zero status on failure
 int device_props(DeviceProps* out);
 
+// One-time (per kernel and device) launch preparation: checks that the kernel was built with at least `min_regs`
+// registers per thread (0 = no check; a setmaxnreg.inc hand-over would otherwise wait forever) and raises its dynamic
+// shared-memory limit to at least `smem_bytes`.  Later calls with the same or a smaller size cost one table lookup.
+int prepare_kernel_impl(const void* kernel, int min_regs, int smem_bytes);
+template <typename K>
+int prepare_kernel(K kernel, int min_regs, int smem_bytes) {
+  return prepare_kernel_impl(reinterpret_cast<const void*>(kernel), min_regs, smem_bytes);
+}
+
 // Arguments of the fused forward, shared by the SIMT and tcgen05 variants.
 struct RqFwdArgs {
   const float* x;
@@ -55,11 +64,9 @@ int launch_rq_fwd_tc(const RqFwdArgs& a, int d, bool rot, void* workspace, size_
                      cudaStream_t stream);
 int launch_rq_pack(const float* codebooks, int n_levels, int k, int d, void* workspace, size_t workspace_bytes,
                    cudaStream_t stream);
-// previous kernel generation, A/B runs only (HIDVAE_TC_IMPL=v4); `packed` = image written by launch_rq_pack
+// streamed operand images (generation 4): D = 16 / 32 / 64, any K; `packed` = image written by launch_rq_pack
 int launch_rq_fwd_tc_v4(const RqFwdArgs& a, int d, bool rot, void* packed, cudaStream_t stream);
-// generation 10 (ticket ring): resident operand images, K <= 256, D = 16 / 32; same packed image
-int launch_rq_fwd_tc_v10(const RqFwdArgs& a, int d, bool rot, const void* packed, cudaStream_t stream);
-bool rq_fwd_tc_v10_supported(int d, int k, int n_levels);
+bool rq_fwd_tc_v4_supported(int d, int k, int n_levels);
 // generation 11 (row owners): D = 32, K <= 256, A operand in tensor memory, fp32 codebooks in shared memory
 int launch_rq_fwd_tc_v11(const RqFwdArgs& a, bool rot, const void* images, const void* cb32, cudaStream_t stream);
 bool rq_fwd_tc_v11_supported(int d, int k, int n_levels);

@@ -8,9 +8,8 @@
 //     Jh  = h                                (STE)      | h - 2 (h.w) w + 2 (h.q) u   (rotation trick)
 //     G   = G + Jh + 2 beta (r_l - e_l) g_loss          | eval: G = G + 2 beta (r_l - e_l) g_loss
 //     gC_l[id_l] += 2 (e_l - r_l) g_loss                | eval: += h + 2 (e_l - r_l) g_loss
-// The codebook gradient is a scatter-add by id (the embedding_dense_backward of modules/quantize.py:97-98):
-// when [L, K, D] fits, it is accumulated with shared-memory atomics per CTA and flushed once, otherwise (or for
-// small N) with global red.add.
+// The codebook gradient is a scatter-add by id (the embedding_dense_backward of modules/quantize.py:97-98): one
+// red.global.add.v4.f32 per lane, spread over zeroed replicas of [L, K, D] for large N (folded by a second tiny kernel).
 #include <stdlib.h>
 
 #include <type_traits>
@@ -45,7 +44,6 @@ struct RqBwdArgs {
   const float* g_level_loss;
   float* g_x;
   float* g_codebooks;
-  int debug;  // HIDVAE_BWD_DEBUG ablation mask (timing experiments only)
   float* replicas;    // [n_replicas, L, K, D] zeroed scratch or null: CTAs spread their reductions over the copies
   int n_replicas;
 };
@@ -72,17 +70,10 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
 template <int D, bool ROT, bool TRAIN, int NL>
 __global__ void __launch_bounds__(kBwdThreads, NL > 0 ? HV_BWD_MINB : 1) rq_bwd_kernel(RqBwdArgs a) {
   constexpr int LMAX = NL > 0 ? NL : kMaxLevels;
-  constexpr bool SMEM_ACC = false;  // shared-memory accumulation measured ATOMS-bound (profiles/README.md); kept for experiments
   constexpr int LPR = D / 4;  // lanes per row
   constexpr int ROWS_PER_WARP = 32 / LPR;
-  extern __shared__ __align__(16) float s_gc[];  // [L, K, D] when SMEM_ACC
 
   const int64_t lkd = static_cast<int64_t>(a.n_levels) * a.k * D;
-  if (SMEM_ACC) {
-    for (int64_t i = threadIdx.x; i < lkd; i += kBwdThreads) s_gc[i] = 0.f;
-    __syncthreads();
-  }
-
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
   const int warp_global = (blockIdx.x * kBwdThreads + threadIdx.x) >> 5;
@@ -106,7 +97,6 @@ __global__ void __launch_bounds__(kBwdThreads, NL > 0 ? HV_BWD_MINB : 1) rq_bwd_
         int64_t code = a.ids[rrow * a.ids_row_stride + l * a.ids_level_stride];
         code = code < 0 ? 0 : (code >= a.k ? a.k - 1 : code);
         id[l] = static_cast<int>(code);
-        if (a.debug & 2) code = (row + 7 * l) & (a.k - 1);
         const float4 e = __ldg(reinterpret_cast<const float4*>(a.codebooks + (static_cast<int64_t>(l) * a.k + code) * D) + sub);
         R[l] = r;
         E[l] = e;
@@ -188,27 +178,11 @@ __global__ void __launch_bounds__(kBwdThreads, NL > 0 ? HV_BWD_MINB : 1) rq_bwd_
         }
         if (valid) {
           const int64_t off = (static_cast<int64_t>(l) * a.k + id[l]) * D + sub * 4;
-          if (SMEM_ACC) {
-            float* dst = s_gc + off;
-            atomicAdd(dst + 0, ge_code.x);
-            atomicAdd(dst + 1, ge_code.y);
-            atomicAdd(dst + 2, ge_code.z);
-            atomicAdd(dst + 3, ge_code.w);
-          } else {
-            if (!(a.debug & 1)) red_add_v4(gc_base + off, ge_code);
-          }
+          red_add_v4(gc_base + off, ge_code);
         }
       }
     }
     if (valid) reinterpret_cast<float4*>(a.g_x + row * D)[sub] = G;
-  }
-
-  if (SMEM_ACC) {
-    __syncthreads();
-    for (int64_t i = threadIdx.x; i < lkd; i += kBwdThreads) {
-      const float v = s_gc[i];
-      if (v != 0.f) atomicAdd(a.g_codebooks + i, v);
-    }
   }
 }
 
@@ -307,16 +281,12 @@ extern "C" int hv_rq_backward(const float* x, int64_t n, int d, const float* cod
     return HV_ERR_MISALIGNED;
   }
   RqBwdArgs a{x, codebooks, n, n_levels, k, beta, training ? 1 : 0, ids, ids_row_stride, ids_level_stride,
-              g_emb, g_emb_level_stride, g_emb_row_stride, g_loss, g_loss_stride, g_level_loss, g_x, g_codebooks, 0, nullptr, 0};
-  {
-    static const int dbg = [] { const char* e = getenv("HIDVAE_BWD_DEBUG"); return e != nullptr ? atoi(e) : 0; }();
-    a.debug = dbg;
-  }
+              g_emb, g_emb_level_stride, g_emb_row_stride, g_loss, g_loss_stride, g_level_loss, g_x, g_codebooks, nullptr, 0};
   const bool rot = mode == HV_MODE_ROTATION_TRICK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int n_rep = rq_bwd_replicas(n, d, k, n_levels);
   const size_t rep_bytes = rq_bwd_workspace_bytes(n, d, k, n_levels);
-  const bool use_rep = n_rep > 0 && workspace != nullptr && workspace_bytes >= rep_bytes && aligned16(workspace) && !(a.debug & 4);
+  const bool use_rep = n_rep > 0 && workspace != nullptr && workspace_bytes >= rep_bytes && aligned16(workspace);
   if (use_rep) {
     HV_CUDA_CHECK(cudaMemsetAsync(workspace, 0, rep_bytes, s));
     a.replicas = static_cast<float*>(workspace);

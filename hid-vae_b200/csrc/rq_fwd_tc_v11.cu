@@ -492,21 +492,18 @@ int launch_rq_fwd_tc_v11(const RqFwdArgs& a, bool rot, const void* images, const
   if (int st = device_props(&props)) return st;
   const int64_t n_row_tiles = (a.n + kTileRows - 1) / kTileRows;
   const unsigned grid = static_cast<unsigned>(n_row_tiles < props.sm_count ? n_row_tiles : props.sm_count);
-  static const int debug = [] {
+#ifdef HV_TC_INSTRUMENT
+  static const int debug = [] {  // instrumented builds only: bit 64 prints block 0's timeline
     const char* e = getenv("HIDVAE_TC_DEBUG");
     return e != nullptr ? atoi(e) : 0;
   }();
+#else
+  constexpr int debug = 0;
+#endif
   V11Params p{static_cast<const uint8_t*>(images), static_cast<const uint8_t*>(cb32), debug};
   const int smem = smem_bytes(a.n_levels);
   auto go = [&](auto kernel) -> int {
-    cudaFuncAttributes attr;
-    HV_CUDA_CHECK(cudaFuncGetAttributes(&attr, kernel));
-    if (attr.numRegs < kLaunchRegs) {  // setmaxnreg.inc would wait forever: refuse loudly instead
-      set_error("hv_rq_forward: tcgen05 kernel (generation 11) was built with %d registers/thread, the register hand-over needs %d",
-                attr.numRegs, kLaunchRegs);
-      return HV_ERR_UNSUPPORTED;
-    }
-    HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (int st = prepare_kernel(kernel, kLaunchRegs, smem)) return st;
     kernel<<<grid, kThreads, smem, stream>>>(a, p);
     HV_CUDA_CHECK(cudaGetLastError());
     return HV_OK;

@@ -1,5 +1,6 @@
-// PREVIOUS tcgen05 variant (v4) of the fused L-level residual quantiser, kept for A/B runs only
-// (HIDVAE_TC_IMPL=v4).  The shipped kernel is rq_fwd_tc.cu.  Consumes the same operand image (256-code N tiles).
+// tcgen05 kernel of the fused L-level residual quantiser with STREAMED operand images (generation 4): D = 16 / 32 / 64,
+// any K -- every shape generation 11 (rq_fwd_tc_v11.cu: D = 32, K <= 256, resident images) does not serve, notably config
+// C4 (D = 64, K = 4096).  Consumes the operand images written by rq_pack.cu (256-code N tiles).
 //
 // Mapping (re-derived for B200 and revised after the first ncu captures, profiles/):
 //   GEMM  M = 128 rows of one row tile (= the 128 TMEM lanes), N = up to 256 codes, reduction = D.
@@ -70,15 +71,9 @@ bool plan_for(int d, int k, int n_levels, int n_wg, TcPlan* p) {
 
 // The packed image (ntile, tile_bytes) does not depend on n_wg, so pack and forward always agree.
 bool make_plan(int d, int k, int n_levels, TcPlan* p) {
-  if (d % 16 != 0 || d < 16 || d > 128 || k < 1 || n_levels < 1) return false;
+  if ((d != 16 && d != 32 && d != 64) || k < 1 || n_levels < 1) return false;
   // four tiles in flight when the whole operand image stays resident beside four A buffers; else two.
-  // HIDVAE_TC_NWG=2|4 overrides the choice (tuning experiments only).
-  static const int forced = [] {
-    const char* e = getenv("HIDVAE_TC_NWG");
-    return e != nullptr ? atoi(e) : 0;
-  }();
-  if (forced == 2) return plan_for(d, k, n_levels, 2, p);
-  if (plan_for(d, k, n_levels, 4, p) && (p->resident || forced == 4)) return true;
+  if (plan_for(d, k, n_levels, 4, p) && p->resident) return true;
   return plan_for(d, k, n_levels, 2, p);
 }
 
@@ -549,14 +544,7 @@ int launch_wg(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed,
   const unsigned grid = static_cast<unsigned>(n_groups < props.sm_count ? n_groups : props.sm_count);
   TcParams p{packed, plan.ntile, plan.n_ktiles, plan.tile_bytes, plan.stages, plan.resident, plan.a_bytes, static_cast<int>(tpc)};
   auto go = [&](auto kernel) -> int {
-    cudaFuncAttributes attr;
-    HV_CUDA_CHECK(cudaFuncGetAttributes(&attr, kernel));
-    if (attr.numRegs < Roles<NWG>::kLaunchRegs) {  // would deadlock in setmaxnreg.inc: refuse loudly instead
-      set_error("hv_rq_forward: tcgen05 kernel was built with %d registers/thread, the register hand-over needs %d",
-                attr.numRegs, Roles<NWG>::kLaunchRegs);
-      return HV_ERR_UNSUPPORTED;
-    }
-    HV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    if (int st = prepare_kernel(kernel, Roles<NWG>::kLaunchRegs, plan.smem_bytes)) return st;
     kernel<<<grid, Roles<NWG>::kThreads, plan.smem_bytes, stream>>>(a, p);
     HV_CUDA_CHECK(cudaGetLastError());
     return HV_OK;
@@ -573,7 +561,12 @@ int launch_d(const RqFwdArgs& a, bool rot, const TcPlan& plan, uint8_t* packed, 
 
 }  // namespace
 
-// `packed` = image written by launch_rq_pack (rq_fwd_tc.cu)
+bool rq_fwd_tc_v4_supported(int d, int k, int n_levels) {
+  TcPlan plan;
+  return make_plan(d, k, n_levels, &plan);
+}
+
+// `packed` = image written by launch_rq_pack (rq_pack.cu)
 int launch_rq_fwd_tc_v4(const RqFwdArgs& a, int d, bool rot, void* packed, cudaStream_t stream) {
   TcPlan plan;
   if (!make_plan(d, a.k, a.n_levels, &plan)) {
