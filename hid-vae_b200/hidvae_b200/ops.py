@@ -5,11 +5,13 @@ a kernel in libhidvae_b200.so.  Tensors must live on a CUDA device: there is no 
 
 Mirrors, per function, the reference call sequence it replaces:
   rq_forward / RqFunction     modules/quantize.py:106-148 x L levels + modules/h_rqvae.py:515-523,552,572-574
+  encoder_pack / encoder_forward   modules/encoder.py:23-36 (the MLP in front of the quantiser, eval passes)
   kmeans_*                    init/kmeans.py:43-61
   uniqueness_loss / count     modules/h_rqvae.py:41-105, :645-648
 """
 from __future__ import annotations
 
+import ctypes
 from typing import NamedTuple, Optional
 
 import torch
@@ -188,6 +190,58 @@ def rq_encode(x: Tensor, codebooks: Tensor, algo="auto", ids_out: Optional[Tenso
               packed: Optional[Tensor] = None) -> Tensor:
     """Encode-only (eval) semantic IDs [N, L] -- modules/tokenizer/h_semids.py:127-130."""
     return rq_forward(x, codebooks, HV_MODE_STE, False, 0.0, algo=algo, ids_out=ids_out, packed=packed).ids
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused encoder MLP (modules/encoder.py:23-36) -- inference only: training keeps the PyTorch layers (autograd)
+# ------------------------------------------------------------------------------------------------------------------
+def _dims_array(dims):
+    return (ctypes.c_int * len(dims))(*[int(v) for v in dims])
+
+
+def encoder_supported(dims) -> bool:
+    """True when the fused kernel has an instantiation for the MLP widths [in, hidden..., out]."""
+    return int(lib.hv_encoder_workspace_bytes(len(dims) - 1, _dims_array(dims))) > 0
+
+
+class EncoderImage(NamedTuple):
+    data: Tensor          # uint8: the fp16 tensor-core image of every layer's weights
+    dims: tuple           # (in, hidden..., out)
+
+
+def encoder_pack(weights) -> EncoderImage:
+    """fp16 tensor-core image of the Linear weights [out_l, in_l] (hv_encoder_pack_weights).  Pack once per set of
+    weights and pass the result to encoder_forward."""
+    weights = [_f32c(w.detach()) for w in weights]
+    _require_cuda(*weights)
+    dims = [weights[0].shape[1]] + [w.shape[0] for w in weights]
+    arr = _dims_array(dims)
+    nbytes = int(lib.hv_encoder_workspace_bytes(len(weights), arr))
+    if not nbytes:
+        raise _lib.HidvaeError(_lib.HV_ERR_UNSUPPORTED, f"no fused encoder instantiation for widths {dims}")
+    image = torch.empty(nbytes, dtype=torch.uint8, device=weights[0].device)
+    ptrs = (ctypes.c_void_p * len(weights))(*[w.data_ptr() for w in weights])
+    with torch.cuda.device(image.device):
+        check(lib.hv_encoder_pack_weights(ptrs, len(weights), arr, image.data_ptr(), nbytes, _stream(image)))
+    return EncoderImage(image, tuple(int(v) for v in dims))
+
+
+def encoder_forward(x: Tensor, image: EncoderImage, normalize: bool = False, precise_silu: bool = False,
+                    out: Optional[Tensor] = None) -> Tensor:
+    """z [N, out] = the MLP applied to x [N, in] fp32 (hv_encoder_forward): one fused tcgen05 kernel."""
+    image, dims = image.data, image.dims
+    _require_cuda(x, image)
+    x = _f32c(x)
+    if x.dim() != 2 or x.shape[1] != dims[0]:
+        raise ValueError(f"encoder_forward: x {tuple(x.shape)} does not match the encoder input width {dims[0]}")
+    n = x.shape[0]
+    z = out if out is not None else torch.empty((n, dims[-1]), dtype=torch.float32, device=x.device)
+    if z.shape != (n, dims[-1]) or z.dtype != torch.float32 or not z.is_contiguous():
+        raise ValueError("encoder_forward: out must be contiguous fp32 [N, out]")
+    with torch.cuda.device(x.device):
+        check(lib.hv_encoder_forward(x.data_ptr(), n, len(dims) - 1, _dims_array(dims), image.data_ptr(), image.numel(),
+                                     int(bool(normalize)), int(bool(precise_silu)), z.data_ptr(), _stream(x)))
+    return z
 
 
 # ------------------------------------------------------------------------------------------------------------------

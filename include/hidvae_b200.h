@@ -154,6 +154,26 @@ int hv_uniq_backward(const int64_t* ids, int64_t rows, int64_t width, int64_t ro
                      const float* g_out, float* g_feats, void* stream);
 
 /*
+ * Fused encoder MLP in front of the quantiser: z = [l2norm](W_L silu(... silu(W_1 x))) -- the bias-free Linear + SiLU
+ * stack of modules/encoder.py:23-36 as called by HRqVae.encode (modules/h_rqvae.py:599) in eval / bulk-assignment passes
+ * (modules/tokenizer/h_semids.py:127).  One kernel: the chain of GEMMs runs on tcgen05 with the hidden activations kept
+ * in tensor memory.  Operands are rounded to fp16 (TF32-grade significand: the precision of the reference's own GPU path,
+ * modules/h_rqvae.py:21), accumulation and activations are fp32.
+ *   dims        [n_layers + 1] HOST array: input, hidden..., output widths.  Served: {768, 512, 256, 128, 32}; any other
+ *               shape returns HV_ERR_UNSUPPORTED / a zero workspace size (the caller keeps its cuBLAS path).
+ *   weights     HOST array of n_layers DEVICE pointers, layer l = nn.Linear.weight [dims[l+1], dims[l]] fp32 row-major
+ *   workspace   hv_encoder_workspace_bytes(): the fp16 weight image hv_encoder_pack_weights writes once per set of weights
+ *   normalize   1: rows of z are L2-normalised (F.normalize, eps 1e-12; MLP(normalize=True))
+ *   precise_silu  0: x*sigmoid(x) as h + h*tanh(h), h = x/2 (one MUFU op per element); 1: ex2 + rcp form
+ *   z           [N, dims[n_layers]] fp32
+ */
+size_t hv_encoder_workspace_bytes(int n_layers, const int* dims);
+int hv_encoder_pack_weights(const float* const* weights, int n_layers, const int* dims, void* workspace, size_t workspace_bytes,
+                            void* stream);
+int hv_encoder_forward(const float* x, int64_t n, int n_layers, const int* dims, const void* workspace, size_t workspace_bytes,
+                       int normalize, int precise_silu, float* z, void* stream);
+
+/*
  * Data-parallel exchange of a small fp32 buffer (the codebook gradient, train_hidvae.py's DDP all-reduce) as ONE kernel
  * over NVLink / NVSwitch peer memory: every rank pushes its contribution into an inbox slot on every peer, flags it,
  * waits for its peers' flags and sums the slots in rank order (bit-identical results on every rank).

@@ -258,6 +258,27 @@ def make_tokenizer_cases(ref):
     np.savez_compressed(os.path.join(OUT, "tokenizer_cached.npz"), **out)
 
 
+def make_encoder_cases(ref):
+    """The reference's own `MLP` (modules/encoder.py) at the gin shape 768 -> 512 -> 256 -> 128 -> 32, with and without
+    the L2-norm tail, on seeded unit-norm rows.  The weights come from oracle.encoder.seeded_weights(dims, seed) so the
+    fixture carries the seed, not the matrices."""
+    import modules.encoder as ref_encoder
+    from oracle import encoder as OE
+    dims, seed = [768, 512, 256, 128, 32], 2024
+    weights = OE.seeded_weights(dims, seed)
+    gen = torch.Generator().manual_seed(77)
+    x = unit_rows(48, dims[0], gen)
+    out = {"dims": np.asarray(dims), "seed": np.asarray(seed), "x": _np(x)}
+    for normalize in (False, True):
+        mlp = ref_encoder.MLP(input_dim=dims[0], hidden_dims=dims[1:-1], out_dim=dims[-1], normalize=normalize).eval()
+        linears = [m for m in mlp.mlp if isinstance(m, torch.nn.Linear)]
+        with torch.no_grad():
+            for lin, w in zip(linears, weights):
+                lin.weight.copy_(w)
+            out[f"z_norm{int(normalize)}"] = _np(mlp(x))
+    np.savez_compressed(os.path.join(OUT, "encoder.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order for the recorded values
@@ -266,6 +287,7 @@ def main():
     make_rq_cases(ref)
     make_uniqueness_cases(ref)
     make_kmeans_cases(ref)
+    make_encoder_cases(ref)
     import io, contextlib
     with contextlib.redirect_stdout(io.StringIO()):
         make_hrqvae_forward_cases(ref)
