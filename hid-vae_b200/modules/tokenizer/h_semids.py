@@ -9,7 +9,6 @@ large chunks; per chunk one encoder pass and ONE fused L-level kernel write the 
 the preallocated `cached_ids [N, L (+ L_tags)]` table, and the tag heads reuse that launch's per-level embeddings.
 `shard=(rank, world)` assigns a contiguous item range to every rank; `gather_shards` is the only collective.
 """
-import contextlib
 from typing import List, Optional, Tuple
 
 import torch
@@ -35,17 +34,6 @@ def _features_of(dataset, lo: int, hi: int) -> Tensor:
     return torch.stack([r if isinstance(r, Tensor) else torch.as_tensor(r) for r in rows])
 
 
-@contextlib.contextmanager
-def _matmul_tf32(enabled: bool):
-    """fp32 matmuls on TF32 tensor cores inside the block (what 'high' float32 matmul precision selects)."""
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = bool(enabled) or prev
-    try:
-        yield
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
-
-
 class HSemanticIdTokenizer(nn.Module):
     def __init__(
         self,
@@ -67,15 +55,16 @@ class HSemanticIdTokenizer(nn.Module):
         use_concatenated_ids: bool = False,
         use_interleaved_ids: bool = False,
         chunk_items: int = 1 << 18,
-        encoder_tf32: bool = False,
+        encoder_precision: str = "fused",
     ) -> None:
         super().__init__()
         if sum(map(bool, (use_dedup_dim, use_concatenated_ids, use_interleaved_ids))) > 1:
             raise ValueError("use_dedup_dim, use_concatenated_ids and use_interleaved_ids are mutually exclusive")
         # The reference sets torch.set_float32_matmul_precision('high') at import (modules/h_rqvae.py:21), i.e. TF32 encoder
-        # GEMMs on a GPU.  Here fp32 is the default (ids then match the CPU reference bit for bit outside near-ties);
-        # encoder_tf32=True selects the reference's GPU numerics for the bulk pass: 4x the items/s (profiles/README.md).
-        self.encoder_tf32 = encoder_tf32
+        # GEMMs on a GPU.  encoder_precision (modules/encoder.py): "fused" = the one-kernel tcgen05 encoder with fp16
+        # operands (the same 11-bit significand, fp32 accumulation); "tf32" / "fp32" = the PyTorch layers on cuBLAS
+        # ("fp32": ids match the CPU reference bit for bit outside near-ties).
+        self.encoder_precision = encoder_precision
         self.hrq_vae = HRqVae(
             input_dim=input_dim, embed_dim=output_dim, hidden_dims=hidden_dims, codebook_size=codebook_size,
             codebook_kmeans_init=False, codebook_normalize=hrqvae_codebook_normalize, codebook_sim_vq=hrqvae_sim_vq,
@@ -85,6 +74,7 @@ class HSemanticIdTokenizer(nn.Module):
         if hrqvae_weights_path is not None:
             self.hrq_vae.load_pretrained(hrqvae_weights_path)
         self.hrq_vae.eval()
+        self.hrq_vae.encoder.inference_precision = encoder_precision
         self.codebook_size = codebook_size
         self.n_layers = n_layers
         self.use_dedup_dim = use_dedup_dim
@@ -148,8 +138,7 @@ class HSemanticIdTokenizer(nn.Module):
         for lo in range(lo_all, hi_all, self.chunk_items):
             hi = min(lo + self.chunk_items, hi_all)
             x = _features_of(movie_dataset, lo, hi).to(dev, non_blocking=True)
-            with _matmul_tf32(self.encoder_tf32):
-                enc = model.encode(x)
+            enc = model.encode(x)
             rows = table[lo - lo_all: hi - lo_all]
             if fused:
                 ids_view = rows[:, : len(sem_cols)] if contiguous_sem else None

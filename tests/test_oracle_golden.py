@@ -125,3 +125,13 @@ def test_kmeans_matches_reference(golden_dir, name):
     res = OK.kmeans_run(x, k, init_idx=init_idx)
     assert torch.equal(res.assignment, _t(g[f"{name}/assignment"]))
     torch.testing.assert_close(res.centroids, _t(g[f"{name}/centroids"]), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("normalize", [0, 1])
+def test_encoder_oracle_matches_reference_mlp(golden_dir, normalize):
+    """oracle/encoder.py against the reference's own MLP (modules/encoder.py) at the gin shape 768-512-256-128-32."""
+    from oracle import encoder as OE
+    g = _load(golden_dir, "encoder.npz")
+    weights = OE.seeded_weights([int(v) for v in g["dims"]], int(g["seed"]))
+    z = OE.mlp_forward(_t(g["x"]), weights, bool(normalize))
+    torch.testing.assert_close(z, _t(g[f"z_norm{normalize}"]), rtol=1e-5, atol=1e-7)
