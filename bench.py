@@ -1,21 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- RQ encode+train items/s of the HiD-VAE residual-quantisation hot path on B200.
+"""bench.py -- items/s of HiD-VAE's residual-quantisation hot path on B200, through the reference-shaped module API.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--no-sweep]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], "c2"): the Amazon-Beauty-shaped catalogue, 12,101 items, D=32, K=256, L=3,
-beta=0.4, ROTATION_TRICK (configs/h_rqvae_amazon.gin).  ONE STEP = one pass of the hot path over the catalogue:
-    (1) training forward   hv_rq_forward (ids, emb_out, loss)           modules/quantize.py:100-154 x 3 levels
-    (2) fused backward     hv_rq_backward (g_x, g_codebooks)            autograd of the same
-    (3) eval encode        hv_rq_forward (ids only)                     modules/tokenizer/h_semids.py:127-130
-        (independent of (1)-(2) once the operand image is packed: it runs on a side stream beside them)
-`value` = items / second with inputs resident in HBM (C-ABI calls, CUDA events, L2 flushed between steps);
-`e2e`   = the same pass through the public autograd API from PINNED HOST buffers: H2D of the step's inputs, the
-          three kernels, D2H of ids + loss inside the timed region.
-N > 1: every rank owns its own 12,101-item shard (weak scaling, the reference's per-rank batches) and the
-codebook gradient [L, K, D] is all-reduced over NCCL, overlapped with the eval encode.
---impl reference times the oracle port (the reference's PyTorch-CPU algorithm) on the host cores, rank 0 only.
+Workload (BASELINE.json configs[4], "c5": bulk semantic-ID assignment, one GPU's share of the catalogue): a chunk of
+4 Mi synthetic 768-d items per GPU through `HSemanticIdTokenizer.precompute_corpus_ids` (modules/tokenizer/h_semids.py:
+109-195) -- encoder 768-512-256-128-32 (SiLU, L2 norm), 3 levels x 256 codes x dim 32, ids [N, 3] int64 out.  It is the
+largest single-GPU configuration of BASELINE.json; C1 / C2 / C4 and the RQ-only launches are `sweep` entries.
+ONE STEP = one pass over the GPU's 4 Mi items:
+    per 1 Mi-item chunk     hv_encoder_forward  (enc_mlp_kernel: fused tcgen05 GEMM chain)     modules/encoder.py:23-36
+                            hv_rq_forward       (rq_fwd_tc_v11_kernel: fused 3-level quantiser) modules/quantize.py:100-154
+`value` = items / second with the items resident in HBM (12.9 GB: nothing survives in L2 between steps);
+`e2e`   = the same call with the items in PINNED HOST memory: per-chunk H2D copies, the kernels and the D2H copy of the
+          id table are all inside the timed region (PCIe-bound: 3,072 B in and 24 B out per item).
+N > 1: every rank owns its own contiguous shard of 4 Mi items (weak scaling: the catalogue grows with the GPU count, as in
+the 100 M-item job of BASELINE.json); no data-path collective -- the only exchange is ONE all_gather of the id tables
+after the last step, inside the timed region.
+--impl reference times the reference's own CPU algorithm (the oracle port) on the host cores:
+the batch-512 loop of precompute_corpus_ids over a bounded sample of the same catalogue, rank 0 only.
 """
 import argparse
 import json
@@ -34,11 +37,22 @@ for _p in (os.path.join(ROOT, "hid-vae_b200"), ROOT):
 import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
-METRIC = "rq_encode_train_items_per_s"
+METRIC = "rq_encode_items_per_s"
 UNIT = "items/s"
-WORKLOAD = dict(workload="c2: Amazon-Beauty-shaped catalogue pass (train fwd + bwd + eval encode)", n_items=12101,
-                embed_dim=32, codebook_size=256, n_levels=3, beta=0.4, forward_mode="ROTATION_TRICK",
-                l2_between_steps="flushed (256 MiB write)")
+DIMS = [768, 512, 256, 128, 32]
+N_LEVELS, CODEBOOK, EMBED = 3, 256, 32
+ITEMS_PER_GPU = 1 << 22
+CHUNK_ITEMS = 1 << 20
+E2E_ITEMS = 1 << 20            # pinned-host leg: items per step (PCIe-bound; 3.2 GB of pinned memory per rank)
+REF_SAMPLE_ITEMS = 1 << 16     # CPU arms: items per step (batches of 512, like the reference)
+FLOP_ENCODER = 2.0 * sum(a * b for a, b in zip(DIMS[:-1], DIMS[1:]))        # 1,122,304 per item
+FLOP_RQ = 2.0 * N_LEVELS * CODEBOOK * EMBED                                  # 49,152 per item
+BYTES_ITEM = 4 * DIMS[0] + 8 * N_LEVELS                                      # 3,096 per item
+WORKLOAD = dict(workload="c5: bulk semantic-ID assignment, per-GPU chunk of the catalogue through "
+                         "HSemanticIdTokenizer.precompute_corpus_ids (encoder 768-512-256-128-32 + 3x256x32 quantiser)",
+                items_per_gpu_per_step=ITEMS_PER_GPU, chunk_items=CHUNK_ITEMS, input_dim=DIMS[0], hidden_dims=DIMS[1:-1],
+                embed_dim=EMBED, codebook_size=CODEBOOK, n_levels=N_LEVELS, encoder_precision="fused (fp16 operands, fp32 accumulate)",
+                l2_between_steps="inputs larger than L2 (12.9 GB of items per step)")
 MODE_ROT = 3
 
 
@@ -53,18 +67,36 @@ def peaks():
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the three C2 kernels, taken from the committed
-    `ncu --set full` capture of this same step (profiles/r01_traffic.json); {} when the file is missing."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """dram read + write bytes per launch from the committed `ncu --set full` captures (profiles/r02_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.isfile(path):
         with open(path) as f:
-            return json.load(f).get("c2_bytes_per_launch", {})
+            return json.load(f)
     return {}
 
 
-def synth(n, d, k, n_levels, seed, device="cpu"):
-    """unit-norm encoder outputs, uniform(0,1) codebooks with level 0 row-normalised and the
-    later levels centred/scaled to the residual magnitude ("trained-like"), random upstream gradients."""
+def synth_items(n, seed, device):
+    """item embeddings x = l2norm(randn(n, 768)), generated on the target device in slices."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.empty((n, DIMS[0]), dtype=torch.float32, device=device)
+    for lo in range(0, n, 1 << 18):
+        hi = min(lo + (1 << 18), n)
+        x[lo:hi] = F.normalize(torch.randn(hi - lo, DIMS[0], generator=g, device=device), dim=-1)
+    return x
+
+
+def synth_codebook_weights(seed=1):
+    """uniform(0,1) codebooks like the reference init (quantize.py:86-89), later levels centred and scaled to the
+    residual magnitude ("trained-like").  Level 0 is row-normalised by out_proj (codebook_normalize)."""
+    g = torch.Generator().manual_seed(seed)
+    cbs = torch.rand(N_LEVELS, CODEBOOK, EMBED, generator=g)
+    for l in range(1, N_LEVELS):
+        cbs[l] = (cbs[l] - 0.5) * (0.7 * 0.5 ** l)
+    return cbs
+
+
+def synth_rq(n, d, k, n_levels, seed, device="cpu"):
+    """RQ-only inputs of the sweep / CPU legs: unit-norm encoder outputs, trained-like codebooks, upstream gradients."""
     g = torch.Generator().manual_seed(seed)
     x = F.normalize(torch.randn(n, d, generator=g), dim=-1)
     cbs = torch.rand(n_levels, k, d, generator=g)
@@ -74,6 +106,20 @@ def synth(n, d, k, n_levels, seed, device="cpu"):
     g_emb = torch.randn(n_levels, n, d, generator=g) * 0.01
     g_loss = torch.full((n,), 1.0 / n)
     return x.to(device), cbs.to(device), g_emb.to(device), g_loss.to(device)
+
+
+def make_tokenizer(device):
+    from modules.tokenizer.h_semids import HSemanticIdTokenizer
+    from oracle import encoder as OE  # seeded weights only (shared with the CPU arms so both sides encode the same model)
+    tok = HSemanticIdTokenizer(input_dim=DIMS[0], output_dim=EMBED, hidden_dims=DIMS[1:-1], codebook_size=CODEBOOK,
+                               n_layers=N_LEVELS, n_cat_feats=0, hrqvae_codebook_normalize=True, chunk_items=CHUNK_ITEMS,
+                               encoder_precision="fused").to(device)
+    with torch.no_grad():
+        for lin, w in zip([m for m in tok.hrq_vae.encoder.mlp if isinstance(m, torch.nn.Linear)], OE.seeded_weights(DIMS, 2024)):
+            lin.weight.copy_(w)
+        for layer, w in zip(tok.hrq_vae.layers, synth_codebook_weights()):
+            layer.embedding.weight.copy_(w)
+    return tok.eval()
 
 
 class ClockSampler:
@@ -95,9 +141,6 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def mark(self):
-        return time.time()
-
     def stop(self, t0, t1):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
@@ -118,89 +161,193 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def time_steps(fn, steps, warmup, flush=None):
+    """W warm-ups, then K steps each bracketed by CUDA events on the current stream (optionally an L2 flush between
+    steps); returns the per-step milliseconds."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------------------------
-class NativeStep:
-    """The three C-ABI calls of one step on device-resident inputs."""
-    LAUNCHES_PER_STEP = 4  # pack image + train forward + backward + eval encode (the g_codebooks memset is torch's)
+def run_native(args):
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py (native arm) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
+    from hidvae_b200 import ops
 
-    def __init__(self, ops, x, cbs, g_emb, g_loss, beta):
-        self.ops, self.x, self.cbs, self.g_emb, self.g_loss, self.beta = ops, x, cbs, g_emb, g_loss, beta
-        self.side = torch.cuda.Stream()   # the eval encode depends only on x and the packed image: it runs beside
-                                          # the training forward / backward (a fork/join the CUDA graph keeps)
+    pk = peaks()
+    tok = make_tokenizer(dev)
+    n = ITEMS_PER_GPU
+    x = synth_items(n, seed=1000 + rank, device=dev)          # this rank's shard of the catalogue
+    n_chunks = (n + CHUNK_ITEMS - 1) // CHUNK_ITEMS
+    tok.precompute_corpus_ids(x[:CHUNK_ITEMS])                # packs the weight image, sets kernel attributes
+    torch.cuda.synchronize()
 
-    def train_fwd(self, packed):
-        return self.ops.rq_forward(self.x, self.cbs, MODE_ROT, True, self.beta, want_emb=True, want_loss=True, packed=packed)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_mark0 = time.time()
 
-    def bwd(self, ids):
-        return self.ops.rq_backward(self.x, self.cbs, ids, MODE_ROT, True, self.beta, self.g_emb, self.g_loss, None)
+    # ---- value: items resident in HBM; K steps + (N > 1) the final gather, barrier + synchronize on both sides ----
+    step = lambda: tok.precompute_corpus_ids(x)
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        tok.gather_shards()
+        tok.cached_ids = None
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_evs = []
+    ev0.record()
+    for _ in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        step_evs.append((a, b))
+    gather_ms = None
+    if world > 1:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        table = tok.gather_shards()
+        g1.record()
+        assert table.shape == (world * n, N_LEVELS)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        gather_ms = g0.elapsed_time(g1)
+    total_ms = ev0.elapsed_time(ev1)
+    per_step = [a.elapsed_time(b) for a, b in step_evs]
+    tm = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms = float(tm.item())
+    value = world * n * args.steps / (total_ms * 1e-3)
+    t_mark1 = time.time()
 
-    def encode(self, packed):
-        return self.ops.rq_encode(self.x, self.cbs, packed=packed)
+    # ---- e2e: the same call on PINNED HOST items: chunk H2D + kernels + D2H of the id table inside the timed region ----
+    n_e = min(E2E_ITEMS, n)
+    x_host = torch.empty((n_e, DIMS[0]), dtype=torch.float32).pin_memory()
+    x_host.copy_(x[:n_e])
+    ids_host = torch.empty((n_e, N_LEVELS), dtype=torch.int64).pin_memory()
 
-    def __call__(self, comm=None):
-        main = torch.cuda.current_stream()
-        packed = self.ops.pack_codebooks(self.cbs)
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
-            ids = self.encode(packed)
-        out = self.train_fwd(packed)
-        g_x, g_cb = self.bwd(out.ids)
-        if comm is not None:
-            comm.allreduce_async(g_cb, overlap=False)
-            comm.wait()
-        main.wait_stream(self.side)
-        packed.record_stream(self.side)
-        return out, g_x, g_cb, ids
+    def e2e_step():
+        ids_host.copy_(tok.precompute_corpus_ids(x_host), non_blocking=True)
+
+    if world > 1:
+        dist.barrier()
+    e2e_ms = time_steps(e2e_step, args.steps, args.warmup)
+    te = torch.tensor([sum(e2e_ms)], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_total = float(te.item())
+    e2e_value = world * n_e * args.steps / (e2e_total * 1e-3)
+    ids_dev = tok.precompute_corpus_ids(x[:n_e])
+    torch.cuda.synchronize()
+    e2e_same = bool(torch.equal(ids_dev.cpu(), ids_host))      # host-fed and device-resident passes agree bit for bit
+
+    # ---- per-kernel durations at the step's launch shape (CUDA events around each C-ABI call) -> roofline ----
+    model = tok.hrq_vae
+    image = model.encoder._weight_image()
+    cbs = model.effective_codebooks().detach()
+    packed = ops.pack_codebooks(cbs)
+    z = torch.empty((CHUNK_ITEMS, EMBED), device=dev)
+    ids_buf = torch.empty((CHUNK_ITEMS, N_LEVELS), dtype=torch.int64, device=dev)
+    ci = [0]
+
+    def enc_launch():   # walks the shard so that every launch reads fresh items from HBM, as in the step
+        lo = (ci[0] % n_chunks) * CHUNK_ITEMS
+        ci[0] += 1
+        ops.encoder_forward(x[lo:lo + CHUNK_ITEMS], image, normalize=True, out=z)
+
+    reps = 2 * n_chunks
+    t_enc = statistics.mean(time_steps(enc_launch, reps, 3))
+    t_rq = statistics.mean(time_steps(lambda: ops.rq_encode(z, cbs, ids_out=ids_buf, packed=packed), reps, 3))
+    traffic = ncu_traffic()
+    kernels = [
+        dict(kernel="enc_mlp_kernel (fused encoder 768-512-256-128-32)", ms=t_enc, bound="tensor", rows_per_launch=CHUNK_ITEMS,
+             achieved=FLOP_ENCODER * CHUNK_ITEMS / (t_enc * 1e-3) / 1e12, peak=pk["tensor_sustained"], unit="TFLOP/s",
+             hbm_gbs=CHUNK_ITEMS * (4 * DIMS[0] + 4 * EMBED) / (t_enc * 1e-3) / 1e9, traffic=traffic.get("enc_mlp_kernel")),
+        dict(kernel="rq_fwd_tc_v11_kernel (fused 3-level quantiser, ids only)", ms=t_rq, bound="tensor", rows_per_launch=CHUNK_ITEMS,
+             achieved=FLOP_RQ * CHUNK_ITEMS / (t_rq * 1e-3) / 1e12, peak=pk["tensor_sustained"], unit="TFLOP/s",
+             hbm_gbs=CHUNK_ITEMS * (4 * EMBED + 8 * N_LEVELS) / (t_rq * 1e-3) / 1e9, traffic=traffic.get("rq_fwd_tc_v11_kernel_encode")),
+    ]
+    for kk in kernels:
+        kk["frac"] = kk["achieved"] / kk["peak"]
+        kk["frac_of_burst_peak"] = kk["achieved"] / pk["tensor"]
+    dom = max(kernels, key=lambda kk: kk["ms"])
+    step_ms = statistics.mean(per_step)
+    roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
+                    traffic=dom["traffic"], kernel=dom["kernel"], kernel_ms=dom["ms"], rows_per_launch=CHUNK_ITEMS,
+                    algorithmic_flop_per_item=FLOP_ENCODER, frac_of_burst_peak=dom["frac_of_burst_peak"],
+                    share_of_step=dom["ms"] * n_chunks / step_ms,
+                    peak_source=pk["source"] + ", sustained bf16 (the kernel is timed inside a long step; burst = %.1f)" % pk["tensor"],
+                    traffic_source="profiles/r02_traffic.json (ncu --set full, dram read + write per launch of the same shape)",
+                    step=dict(items_per_s=n / (step_ms * 1e-3), tflops=(FLOP_ENCODER + FLOP_RQ) * n / (step_ms * 1e-3) / 1e12,
+                              frac_of_sustained_peak=(FLOP_ENCODER + FLOP_RQ) * n / (step_ms * 1e-3) / 1e12 / pk["tensor_sustained"],
+                              hbm_gbs=BYTES_ITEM * n / (step_ms * 1e-3) / 1e9),
+                    kernels=kernels)
+
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        del x_host
+        sweep = run_sweep(ops, pk, dev)
+
+    clocks = sampler.stop(t_mark0, t_mark1) if sampler else None
+    if rank == 0:
+        cpu = cpu_baseline(budget_s=6.0) if world == 1 else None
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f16 operands / f32 accumulate (encoder GEMMs, TF32-grade); bf16x3 split / f32 (quantiser scores); ids int64",
+                    data="synthetic",
+                    config=dict(WORKLOAD, parallelism=f"dp{world} (item shards, no data-path collective)",
+                                step_ms_min=min(per_step), step_ms_max=max(per_step), step_ms_mean=step_ms,
+                                final_gather_ms=gather_ms,
+                                collective=("one all_gather of the [N, 3] int64 id tables after the last step, inside the timed region"
+                                            if world > 1 else None)),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=n_e * DIMS[0] * 4, d2h_bytes_per_step=n_e * N_LEVELS * 8,
+                             ms_per_step=e2e_total / args.steps, items_per_step_per_gpu=n_e,
+                             call="HSemanticIdTokenizer.precompute_corpus_ids(pinned host tensor) + id table -> pinned host",
+                             ids_equal_device_resident_pass=e2e_same,
+                             pcie_gbs=(n_e * (DIMS[0] * 4 + N_LEVELS * 8)) / (e2e_total / args.steps * 1e-3) / 1e9),
+                    gpu_launches=(2 * n_chunks + 1) * args.steps, roofline=roofline, cpu_baseline=cpu, clocks=clocks, impl="native")
+        if sweep is not None:
+            line["sweep"] = sweep
+        OUT.emit(json.dumps(line))
+    if world > 1:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)   # (tearing NCCL down was seen to hang on 2 x B200 with NCCL 2.28.9; nothing is pending here)
 
 
-class GradComm:
-    """Codebook-gradient all-reduce.  Default: the one-kernel exchange over NVLink peer memory
-    (hidvae_b200.dist.PeerAllReduce -> hv_peer_allreduce); HIDVAE_BENCH_NCCL=1 (or a node without symmetric-memory
-    support) uses NCCL.  Either runs on a side stream so that it overlaps the eval encode and the step's D2H copies."""
-
-    def __init__(self, numel, device):
-        import torch.distributed as dist
-        self.dist = dist
-        self.stream = torch.cuda.Stream()
-        self.peer, self.pending = None, False
-        if os.environ.get("HIDVAE_BENCH_NCCL", "0") != "1":
-            try:
-                from hidvae_b200.dist import PeerAllReduce
-                self.peer = PeerAllReduce(numel, device)
-            except Exception as e:  # noqa: BLE001
-                print(f"[bench] peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
-        flag = torch.tensor([1 if self.peer is not None else 0], device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank must take the same path
-        if int(flag.item()) == 0:
-            self.peer = None
-        self.kind = "peer-memory one-shot kernel (hv_peer_allreduce)" if self.peer is not None else "nccl"
-
-    def allreduce_async(self, t, overlap=True):
-        """overlap=True: on a side stream (beside the step's D2H copies); False: the peer kernel in line on the current
-        stream (measured 2 us shorter for the device-resident step, where only the eval encode runs beside it)."""
-        self.pending = overlap or self.peer is None
-        if not self.pending:
-            self.peer(t.view(-1))
-            return
-        self.stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.stream):
-            if self.peer is not None:
-                self.peer(t.view(-1))
-            else:
-                self.dist.all_reduce(t)
-        t.record_stream(self.stream)
-
-    def wait(self):
-        if self.pending:
-            torch.cuda.current_stream().wait_stream(self.stream)
-
-
+# ------------------------------------------------------------------------------------------------------------------
+# sweep: the other BASELINE.json shapes and the RQ-only launches (supplementary, N = 1 only)
+# ------------------------------------------------------------------------------------------------------------------
 class GraphedStep:
-    """The step captured once into a CUDA graph and replayed: the C2 step is a handful of microsecond-scale
-    launches, so the CPU-side launch path (ctypes + allocator) would otherwise be what is measured."""
-
     def __init__(self, fn):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -218,311 +365,191 @@ class GraphedStep:
         return self.out
 
 
-def time_region(fn, steps, warmup, flush):
-    """W warm-ups, then K steps each bracketed by CUDA events on the current stream, L2 flushed between steps."""
-    for _ in range(warmup):
-        fn()
-    torch.cuda.synchronize()
-    evs = []
-    for _ in range(steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        fn()
-        b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    return sum(a.elapsed_time(b) for a, b in evs)  # ms
-
-
-def run_native(args):
-    import torch.distributed as dist
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    assert torch.cuda.is_available(), "bench.py (native arm) needs a CUDA device; there is no CPU fallback"
-    torch.cuda.set_device(local)
-    if world > 1:
-        import datetime
-        # a stuck collective must abort the run, not hang it (the watchdog raises after 3 minutes)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
-    from hidvae_b200 import ops
-
-    w = WORKLOAD
-    n, d, k, L, beta = w["n_items"], w["embed_dim"], w["codebook_size"], w["n_levels"], w["beta"]
-    x, cbs, g_emb, g_loss = synth(n, d, k, L, seed=rank, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    step = NativeStep(ops, x, cbs, g_emb, g_loss, beta)
-    comm = GradComm(cbs.numel(), cbs.device) if world > 1 else None
-    pk = peaks()
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    eager = lambda: step(comm)
-    run_step, graphed = eager, False
-    if not args.no_graph:
-        try:
-            run_step, graphed = GraphedStep(eager), True
-        except Exception as e:  # e.g. a collective that cannot be captured: fall back to eager launches
-            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
-            torch.cuda.synchronize()
-    t_mark0 = time.time()
-    total_ms = time_region(run_step, args.steps, args.warmup, flush)
-    eager_ms = time_region(eager, min(args.steps, 100), 3, flush) / min(args.steps, 100) if graphed else None
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_mark1 = time.time()
-    tm = torch.tensor([total_ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms = float(tm.item())
-    value = world * n * args.steps / (total_ms * 1e-3)
-
-    # ---- end to end through the public autograd API from pinned host memory (H2D + kernels + D2H per step) ----
-    x_h = x.cpu().pin_memory()
-    tgt_h = F.normalize(torch.randn(n, d, generator=torch.Generator().manual_seed(99)), dim=-1).pin_memory()
-    ids_h = torch.empty((n, L), dtype=torch.int64).pin_memory()
-    enc_h = torch.empty((n, L), dtype=torch.int64).pin_memory()
-    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
-    cb_param = cbs.clone().requires_grad_(True)
-
-    side = torch.cuda.Stream()
-    feed = torch.cuda.Stream()
-    # Double-buffered input feed (what a DataLoader with pinned-memory prefetch does): the H2D copy of step i+1's inputs
-    # runs on its own stream beside step i's kernels.  EVERY step still issues one H2D of its inputs' size and one D2H of
-    # its results inside its timed region; `serial_ms_per_step` below is the same step with the copy in front of the kernels.
-    x_dev = [torch.empty((n, d), device="cuda").requires_grad_(True) for _ in range(2)]
-    tg_dev = [torch.empty((n, d), device="cuda") for _ in range(2)]
-
-    def e2e_step(j=0, prefetch=False):
-        main = torch.cuda.current_stream()
-        cur, nxt = j & 1, (j & 1) ^ 1
-        if prefetch:
-            feed.wait_stream(main)                                          # (the previous step has released buffer `nxt`)
-            with torch.cuda.stream(feed), torch.no_grad():
-                x_dev[nxt].copy_(x_h, non_blocking=True)
-                tg_dev[nxt].copy_(tgt_h, non_blocking=True)
-        else:
-            with torch.no_grad():
-                x_dev[cur].copy_(x_h, non_blocking=True)
-                tg_dev[cur].copy_(tgt_h, non_blocking=True)
-        xd, tg = x_dev[cur], tg_dev[cur]
-        packed = ops.pack_codebooks(cb_param.detach())
-        side.wait_stream(main)
-        with torch.cuda.stream(side):                                       # eval encode + its D2H beside the training step
-            enc = ops.rq_encode(xd.detach(), cb_param.detach(), packed=packed)
-            enc_h.copy_(enc, non_blocking=True)
-        emb, _res, ids, loss, _ll = ops.RqFunction.apply(xd, cb_param, MODE_ROT, True, beta, "auto")
-        total = ((emb.sum(0) - tg) ** 2).sum(-1).mean() + loss.mean()      # h_rqvae.py:607-640 shaped consumer
-        cb_param.grad = None
-        xd.grad = None
-        total.backward()
-        if comm is not None:
-            comm.allreduce_async(cb_param.grad)
-        ids_h.copy_(ids, non_blocking=True)
-        loss_h.copy_(total.detach(), non_blocking=True)
-        if comm is not None:
-            comm.wait()
-        main.wait_stream(side)
-        if prefetch:
-            main.wait_stream(feed)
-        for t_ in (packed, enc):
-            t_.record_stream(side)
-
-    class Alternating:
-        """Steps 0, 1, 0, 1, ... (one captured graph per input buffer)."""
-
-        def __init__(self, even, odd):
-            self.fns, self.j = (even, odd), 0
-
-        def __call__(self):
-            self.fns[self.j & 1]()
-            self.j += 1
-
-    if world > 1:
-        dist.barrier()
-    # the public API is graph-capturable (no host-side data-dependent branches, every call on the current stream):
-    # a training loop with static shapes replays ONE graph per step -- pinned-host H2D, kernels, D2H included
-    with torch.no_grad():
-        x_dev[0].copy_(x_h)
-        tg_dev[0].copy_(tgt_h)
-    e2e_run, e2e_graphed = Alternating(lambda: e2e_step(0, True), lambda: e2e_step(1, True)), False
-    e2e_serial = lambda: e2e_step(0, False)
-    if not args.no_graph:
-        try:
-            e2e_run = Alternating(GraphedStep(lambda: e2e_step(0, True)), GraphedStep(lambda: e2e_step(1, True)))
-            e2e_serial = GraphedStep(lambda: e2e_step(0, False))
-            e2e_graphed = True
-        except Exception as e:
-            print(f"[bench] e2e CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager calls", file=sys.stderr)
-            torch.cuda.synchronize()
-    ser_steps = min(args.steps, 100)
-    e2e_serial_ms = time_region(e2e_serial, ser_steps, 3, flush) / ser_steps
-    with torch.no_grad():                                                   # buffer 0 holds the first step's inputs
-        x_dev[0].copy_(x_h)
-        tg_dev[0].copy_(tgt_h)
-    torch.cuda.synchronize()
-    e2e_ms = time_region(e2e_run, args.steps, args.warmup, flush)
-    e2e_eager_ms = time_region(lambda: e2e_step(0, False), min(args.steps, 100), 3, flush) / min(args.steps, 100) if e2e_graphed else None
-    te = torch.tensor([e2e_ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
-    e2e_value = world * n * args.steps / (e2e_ms * 1e-3)
-    h2d = x_h.numel() * 4 + tgt_h.numel() * 4
-    d2h = ids_h.numel() * 8 + enc_h.numel() * 8 + 4
-
-    # ---- per-kernel durations inside the same workload (CUDA events around each C-ABI call) -> roofline ----
-    packed = ops.pack_codebooks(cbs)
-    out = step.train_fwd(packed)
-    ksteps = max(10, min(args.steps, 200))
-    t_fwd = time_region(lambda: step.train_fwd(packed), ksteps, 3, flush) / ksteps
-    t_bwd = time_region(lambda: step.bwd(out.ids), ksteps, 3, flush) / ksteps
-    t_enc = time_region(lambda: step.encode(packed), ksteps, 3, flush) / ksteps
-    flops = 2.0 * k * d * L * n                                  # SURVEY 8d: L*2*K*D per item
-    b_enc = n * (4 * d + 8 * L)
-    b_fwd = n * (4 * d + 4 * d * L + 8 * L + 4)
-    b_bwd = n * (4 * d + 8 * L + 4 * d * L + 4 + 4 * d) + 4 * L * k * d
-    kernels = [
-        dict(kernel="rq_fwd_tc_v11_kernel<rot> (train forward)", ms=t_fwd, bound="tensor", achieved=flops / (t_fwd * 1e-3) / 1e12,
-             peak=pk["tensor"], unit="TFLOP/s", hbm_gbs=b_fwd / (t_fwd * 1e-3) / 1e9),
-        dict(kernel="rq_bwd_kernel<32,rot> (backward)", ms=t_bwd, bound="hbm", achieved=b_bwd / (t_bwd * 1e-3) / 1e9, peak=pk["hbm"],
-             unit="GB/s"),
-        dict(kernel="rq_fwd_tc_v11_kernel (eval encode)", ms=t_enc, bound="tensor", achieved=flops / (t_enc * 1e-3) / 1e12,
-             peak=pk["tensor"], unit="TFLOP/s", hbm_gbs=b_enc / (t_enc * 1e-3) / 1e9),
-    ]
-    traffic = ncu_traffic()
-    for kk, key in zip(kernels, ("train_forward", "backward", "eval_encode")):
-        kk["frac"] = kk["achieved"] / kk["peak"]
-        kk["traffic"] = traffic.get(key)
-    dom = max(kernels, key=lambda kk: kk["ms"])
-    roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
-                    traffic=dom.get("traffic"), traffic_source="profiles/r01_traffic.json (ncu --set full, dram read + write per launch)",
-                    kernel=dom["kernel"], kernel_ms=dom["ms"], peak_source=pk["source"] + ", burst",
-                    kernels=kernels)
-
-    sweep = None
-    if rank == 0 and not args.no_sweep:
-        sweep = run_sweep(ops, pk, flush)
-
-    clocks = sampler.stop(t_mark0, t_mark1) if sampler else None
-    cpu = None
-    if rank == 0:
-        cpu = cpu_baseline(n, d, k, L, beta, budget_s=12.0)
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f32 (argmin scores: bf16x3 split on tcgen05, fp32 accumulate)", data="synthetic",
-                    config=dict(WORKLOAD, parallelism=f"dp{world}", items_per_step_per_gpu=n, cuda_graph=graphed,
-                                eager_ms_per_step=eager_ms, grad_allreduce=(comm.kind if comm is not None else None)),
-                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             ms_per_step=e2e_ms / args.steps, cuda_graph=e2e_graphed, eager_ms_per_step=e2e_eager_ms,
-                             input_feed="double-buffered: step i+1's pinned-host H2D on a copy stream beside step i's kernels; one H2D + one D2H per timed step",
-                             serial_ms_per_step=e2e_serial_ms),
-                    gpu_launches=(NativeStep.LAUNCHES_PER_STEP + (1 if comm is not None and comm.peer is not None else 0)) * args.steps, roofline=roofline, cpu_baseline=cpu,
-                    clocks=clocks, impl="native")
-        if sweep is not None:
-            line["sweep"] = sweep
-        OUT.emit(json.dumps(line))
-    if world > 1:
-        # No collective is pending (every rank passed the last all-reduce before rank 0 started its CPU baseline).
-        # The captured graphs still hold NCCL kernels, and tearing the communicator down under them was seen to hang
-        # (2 x B200, NCCL 2.28.9): drop the graphs, drain the device and leave without the NCCL teardown.
-        del run_step, e2e_run
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
-
-
-def run_sweep(ops, pk, flush):
-    """Supplementary single-kernel numbers on the other BASELINE.json shapes (not bench lines; parity cases whose
-    roofline fraction is informative because the launch is long enough to fill the machine)."""
+def run_sweep(ops, pk, dev):
     res = []
-    for name, (n, d, k, L) in {"c1_batch1024": (1024, 32, 256, 3), "c5_chunk_4Mi": (1 << 22, 32, 256, 3),
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    mean = lambda fn, reps, fl=None: statistics.mean(time_steps(fn, reps, 3, fl))
+
+    # RQ-only launches: C1 batch, the C5 chunk on 32-d encoder outputs, C4
+    for name, (n, d, k, L) in {"c1_batch1024_rq_only": (1024, 32, 256, 3), "c5_rq_only_4Mi": (1 << 22, 32, 256, 3),
                                "c4_65536x64x4096x4": (65536, 64, 4096, 4)}.items():
-        x, cbs, g_emb, g_loss = synth(n, d, k, L, seed=7, device="cuda")
+        x, cbs, g_emb, g_loss = synth_rq(n, d, k, L, seed=7, device=dev)
         packed = ops.pack_codebooks(cbs)
         fl = None if n * d * 4 > (128 << 20) else flush
-        fb = flush if fl is not None else torch.empty(1, dtype=torch.uint8, device="cuda")
-        reps = 20
-        t_enc = time_region(lambda: ops.rq_encode(x, cbs, packed=packed), reps, 3, fb) / reps
+        t_enc = mean(lambda: ops.rq_encode(x, cbs, packed=packed), 20, fl)
         ent = dict(case=name, n=n, d=d, k=k, L=L, encode_ms=t_enc, encode_items_per_s=n / (t_enc * 1e-3),
                    encode_tflops=2.0 * k * d * L * n / (t_enc * 1e-3) / 1e12)
-        ent["encode_frac_of_bf16_peak"] = ent["encode_tflops"] / pk["tensor"]
-        if name != "c4_65536x64x4096x4":
+        ent["encode_frac_of_bf16_burst"] = ent["encode_tflops"] / pk["tensor"]
+        ent["encode_frac_of_bf16_sustained"] = ent["encode_tflops"] / pk["tensor_sustained"]
+        if d == 32:
             out = ops.rq_forward(x, cbs, MODE_ROT, True, 0.4, want_emb=True, want_loss=True, packed=packed)
-            t_f = time_region(lambda: ops.rq_forward(x, cbs, MODE_ROT, True, 0.4, want_emb=True, want_loss=True, packed=packed),
-                              reps, 3, fb) / reps
-            t_b = time_region(lambda: ops.rq_backward(x, cbs, out.ids, MODE_ROT, True, 0.4, g_emb, g_loss, None), reps, 3, fb) / reps
+            t_f = mean(lambda: ops.rq_forward(x, cbs, MODE_ROT, True, 0.4, want_emb=True, want_loss=True, packed=packed), 20, fl)
+            t_b = mean(lambda: ops.rq_backward(x, cbs, out.ids, MODE_ROT, True, 0.4, g_emb, g_loss, None), 20, fl)
             byt = n * (4 * d * (3 + 2 * L) + 16 * L + 8)
             ent.update(train_fwd_ms=t_f, train_bwd_ms=t_b, train_items_per_s=n / ((t_f + t_b) * 1e-3),
                        train_hbm_gbs=byt / ((t_f + t_b) * 1e-3) / 1e9)
             ent["train_frac_of_hbm_peak"] = ent["train_hbm_gbs"] / pk["hbm"]
         res.append(ent)
         del x, cbs, g_emb, g_loss
+
+    # C2: the Amazon-Beauty-shaped catalogue pass of round 1 (train forward + backward + eval encode, one CUDA graph)
+    n, d, k, L, beta = 12101, 32, 256, 3, 0.4
+    x, cbs, g_emb, g_loss = synth_rq(n, d, k, L, seed=0, device=dev)
+    side = torch.cuda.Stream()
+
+    def c2_step():
+        main = torch.cuda.current_stream()
+        packed = ops.pack_codebooks(cbs)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ids = ops.rq_encode(x, cbs, packed=packed)
+        out = ops.rq_forward(x, cbs, MODE_ROT, True, beta, want_emb=True, want_loss=True, packed=packed)
+        g = ops.rq_backward(x, cbs, out.ids, MODE_ROT, True, beta, g_emb, g_loss, None)
+        main.wait_stream(side)
+        packed.record_stream(side)
+        return out, g, ids
+
+    graphed = GraphedStep(c2_step)
+    t_c2 = mean(graphed, 200, flush)
+    res.append(dict(case="c2_catalogue_pass_12101_items (train fwd + bwd + eval encode, CUDA graph)", n=n, ms=t_c2,
+                    items_per_s=n / (t_c2 * 1e-3), eager_ms=mean(c2_step, 50, flush)))
+    del graphed
+
+    # C1 through the module API: HRqVae.forward + backward, batch 1024, 768-d items, rotation trick, untagged
+    from data.schemas import SeqBatch
+    from modules.h_rqvae import HRqVae
+    from modules.quantize import QuantizeForwardMode
+    model = HRqVae(input_dim=768, embed_dim=32, hidden_dims=[512, 256, 128], codebook_size=256, codebook_kmeans_init=False,
+                   codebook_normalize=True, codebook_mode=QuantizeForwardMode.ROTATION_TRICK, n_layers=3, n_cat_features=0,
+                   commitment_weight=0.4, tag_class_counts=[38, 168, 348]).to(dev).train()
+    xb = synth_items(1024, seed=5, device=dev)
+    batch = SeqBatch(user_ids=None, ids=None, ids_fut=None, x=xb, x_fut=None, seq_mask=None)
+
+    def c1_step():
+        model.zero_grad(set_to_none=True)
+        model(batch, gumbel_t=0.2).loss.backward()
+
+    t_c1 = mean(c1_step, 30, flush)
+    res.append(dict(case="c1_HRqVae.forward+backward_batch1024_untagged (module API, eager PyTorch MLPs + fused RQ)", n=1024,
+                    ms=t_c1, items_per_s=1024 / (t_c1 * 1e-3)))
     return res
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm (the one place besides tests/smoke that may execute oracle/)
+# CPU arms: the oracle port of the reference algorithm (the one place besides tests/smoke that may execute oracle/)
 # ------------------------------------------------------------------------------------------------------------------
-def oracle_step(O, x, cb_list, tgt, beta):
-    xg = x.clone().requires_grad_(True)
-    cbs = [c.clone().requires_grad_(True) for c in cb_list]
-    out = O.rq_forward(xg, cbs, O.MODE_ROTATION_TRICK, beta, True)
-    total = ((out.embeddings.sum(-1) - tgt) ** 2).sum(-1).mean() + out.quantize_loss.mean()
-    total.backward()
-    with torch.no_grad():
-        enc = O.rq_forward(x, cb_list, O.MODE_ROTATION_TRICK, beta, False)
-    return float(total.detach()), enc.sem_ids
+def _cpu_model():
+    from oracle import encoder as OE
+    from oracle import rq as O
+    enc_w = OE.seeded_weights(DIMS, 2024)
+    cb_w = synth_codebook_weights()
+    cbs = [O.effective_codebook(cb_w[l], l == 0) for l in range(N_LEVELS)]
+    return enc_w, cb_w, cbs
 
 
-def cpu_baseline(n, d, k, L, beta, budget_s):
+def _timed(fn, budget_s, min_reps=3, max_reps=200, warm=1):
+    for _ in range(warm):
+        fn()
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < min_reps or (time.perf_counter() < t_end and len(times) < max_reps):
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+    return statistics.median(times), len(times)
+
+
+def cpu_baseline(budget_s):
+    """The five CPU legs of BASELINE.md section 3 on this box's host cores (oracle port, torch CPU, all threads); `value`
+    is the leg that matches the headline workload: the batch-512 precompute_corpus_ids loop."""
+    from oracle import encoder as OE
+    from oracle import hrqvae as OH
+    from oracle import kmeans as OK
     from oracle import rq as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    x, cbs, _, _ = synth(n, d, k, L, seed=0)
-    tgt = F.normalize(torch.randn(n, d, generator=torch.Generator().manual_seed(99)), dim=-1)
-    cb_list = [cbs[l] for l in range(L)]
-    oracle_step(O, x, cb_list, tgt, beta)
-    oracle_step(O, x, cb_list, tgt, beta)
-    t0, reps = time.perf_counter(), 0
-    while reps < 10 or (time.perf_counter() - t0 < budget_s and reps < 400):
-        oracle_step(O, x, cb_list, tgt, beta)
-        reps += 1
+    enc_w, cb_w, cbs = _cpu_model()
+    legs = {}
+    # (iv) the headline workload: precompute_corpus_ids loop, batch 512, encoder + quantiser
+    xs = synth_items(REF_SAMPLE_ITEMS, seed=1000, device="cpu")
+    t, reps = _timed(lambda: OH.precompute_corpus_ids(xs, enc_w, cbs, True), budget_s, min_reps=2)
+    value = REF_SAMPLE_ITEMS / t
+    legs["precompute_corpus_ids_batch512_65536_items"] = dict(items_per_s=value, ms=t * 1e3, reps=reps)
+    # (i) C1 untagged HRqVae.forward + backward, batch 1024 (the tagged variant needs the tag heads, which are outside the
+    #     hot path and have no oracle port: SURVEY section 2 row 11)
+    dec_w = OE.seeded_weights(DIMS[::-1], 2025)
+    x1 = xs[:1024]
+    for mname, mode in (("ste", O.MODE_STE), ("rotation", O.MODE_ROTATION_TRICK)):
+        params = [w.clone().requires_grad_(True) for w in (*enc_w, *dec_w, *cb_w)]
+        ew, dw, cw = params[:4], params[4:8], params[8:]
+
+        def step(mode=mode, ew=ew, dw=dw, cw=cw, params=params):
+            for p in params:
+                p.grad = None
+            OH.untagged_step(x1, ew, dw, cw, mode, 0.4, True).backward()
+
+        t, reps = _timed(step, budget_s / 3)
+        legs[f"c1_hrqvae_forward_backward_untagged_{mname}"] = dict(items_per_s=1024 / t, ms=t * 1e3, reps=reps)
+    # (ii) C1 RQ-only get_semantic_ids forward + backward
+    xr, cr, _, _ = synth_rq(1024, 32, 256, 3, seed=7)
+    for mname, mode in (("ste", O.MODE_STE), ("rotation", O.MODE_ROTATION_TRICK)):
+        def step(mode=mode):
+            xg = xr.clone().requires_grad_(True)
+            cg = [cr[l].clone().requires_grad_(True) for l in range(3)]
+            out = O.rq_forward(xg, cg, mode, 0.4, True)
+            (out.embeddings.sum() + out.quantize_loss.sum()).backward()
+
+        t, reps = _timed(step, budget_s / 4)
+        legs[f"c1_rq_only_forward_backward_{mname}"] = dict(items_per_s=1024 / t, ms=t * 1e3, reps=reps)
+    # (iii) eval encode at 65,536 rows: C1 shape, and C4 shape on a reduced row count (the [N, 4096] fp32 tables)
+    xe, ce, _, _ = synth_rq(65536, 32, 256, 3, seed=7)
+    with torch.no_grad():
+        t, reps = _timed(lambda: O.rq_forward(xe, [ce[l] for l in range(3)], O.MODE_STE, 0.25, False), budget_s / 3, min_reps=2)
+        legs["eval_encode_rq_only_65536x32_k256_l3"] = dict(items_per_s=65536 / t, ms=t * 1e3, reps=reps)
+        x4, c4, _, _ = synth_rq(16384, 64, 4096, 4, seed=7)
+        t, reps = _timed(lambda: O.rq_forward(x4, [c4[l] for l in range(4)], O.MODE_STE, 0.25, False), budget_s / 3, min_reps=2, warm=0)
+        legs["eval_encode_rq_only_c4_shape_16384x64_k4096_l4 (N reduced from 65,536)"] = dict(items_per_s=16384 / t, ms=t * 1e3, reps=reps)
+    # (v) Kmeans.run on 20,000 x 32, K = 256, fixed seed; bounded to 8 Lloyd iterations (the reference runs to 1e-10)
+    xk = F.normalize(torch.randn(20000, 32, generator=torch.Generator().manual_seed(3)), dim=-1)
+    import numpy as np
+    init_idx = np.random.RandomState(0).choice(20000, 256, replace=False)
+    t0 = time.perf_counter()
+    km = OK.kmeans_run(xk, 256, max_iters=8, init_idx=init_idx)
     dt = time.perf_counter() - t0
-    return dict(value=n * reps / dt, unit=UNIT, cores=cores, kind="port",
-                sample=f"{reps} full steps of the same 12,101-item workload (oracle/rq.py, torch CPU, {cores} threads)")
+    legs["kmeans_20000x32_k256"] = dict(ms_per_lloyd_iteration=dt / max(km.n_iters, 1) * 1e3, iterations=km.n_iters, total_ms=dt * 1e3,
+                                        note="bounded to 8 Lloyd iterations; the reference runs to max shift < 1e-10 (51 iterations in the survey)")
+    return dict(value=value, unit=UNIT, cores=cores, kind="port",
+                sample=f"{REF_SAMPLE_ITEMS} items of the same synthetic catalogue per pass, batches of 512 (oracle/hrqvae.py "
+                       f"precompute_corpus_ids: encoder + quantiser, torch {torch.__version__} CPU, {cores} threads)",
+                legs=legs)
 
 
 def run_reference(args):
     """The reference's own CPU algorithm (oracle port) on this box's host cores; rank 0 only."""
     if int(os.environ.get("RANK", 0)) != 0:
         return
-    from oracle import rq as O
-    w = WORKLOAD
-    n, d, k, L, beta = w["n_items"], w["embed_dim"], w["codebook_size"], w["n_levels"], w["beta"]
+    from oracle import hrqvae as OH
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    x, cbs, _, _ = synth(n, d, k, L, seed=0)
-    tgt = F.normalize(torch.randn(n, d, generator=torch.Generator().manual_seed(99)), dim=-1)
-    cb_list = [cbs[l] for l in range(L)]
-    steps = min(args.steps, 200)   # bounded sample: every step is the full 12,101-item pass
-    for _ in range(min(args.warmup, 5)):
-        oracle_step(O, x, cb_list, tgt, beta)
+    enc_w, _cb_w, cbs = _cpu_model()
+    xs = synth_items(REF_SAMPLE_ITEMS, seed=1000, device="cpu")
+    steps, warmup = max(1, min(args.steps, 100)), min(args.warmup, 5)
+    for _ in range(warmup):
+        OH.precompute_corpus_ids(xs, enc_w, cbs, True)
     t0 = time.perf_counter()
     for _ in range(steps):
-        oracle_step(O, x, cb_list, tgt, beta)
+        OH.precompute_corpus_ids(xs, enc_w, cbs, True)
     dt = time.perf_counter() - t0
-    value = n * steps / dt
-    sample = f"{steps} full steps of the 12,101-item workload (oracle/rq.py, torch {torch.__version__} CPU, {cores} threads)"
-    OUT.emit(json.dumps(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 5),
-                          ms_per_step=dt / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                          dtype="f32", data="synthetic", config=dict(WORKLOAD, parallelism="cpu"), impl="reference",
-                          cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
-                          e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+    value = REF_SAMPLE_ITEMS * steps / dt
+    sample = (f"{steps} steps x {REF_SAMPLE_ITEMS} items of the same synthetic catalogue, batches of 512 like the reference "
+              f"(oracle/hrqvae.py, torch {torch.__version__} CPU, {cores} threads)")
+    OUT.emit(json.dumps(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup,
+                             ms_per_step=dt / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                             dtype="f32", data="synthetic",
+                             config=dict(WORKLOAD, parallelism="cpu", items_per_gpu_per_step=REF_SAMPLE_ITEMS, chunk_items=512,
+                                         encoder_precision="fp32"),
+                             impl="reference", cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+                             e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
 
 class QuietStdout:
@@ -553,12 +580,13 @@ def main():
     global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-sweep", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
+    ap.add_argument("--chunk-items", type=int, default=CHUNK_ITEMS, help="items per launch inside precompute_corpus_ids (tuning runs)")
     args = ap.parse_args()
+    globals()["CHUNK_ITEMS"] = WORKLOAD["chunk_items"] = args.chunk_items
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     with QuietStdout() as OUT:
         if args.impl == "reference":

@@ -260,7 +260,12 @@ class HRqVae(nn.Module, _HubMixin):
 
     # ---- the hot path -------------------------------------------------------------------------------------------
     def _can_fuse(self) -> bool:
-        return (self.fuse_levels and all(layer.fused and not layer.needs_kmeans() for layer in self.layers))
+        """All L levels in one launch: L2 distance, no pending k-means init, and STE / rotation trick -- or eval mode,
+        whose semantics do not depend on the forward mode (emb_out = codebook[ids], quantize.py:146-148)."""
+        from modules.quantize import QuantizeDistance
+        return self.fuse_levels and all(
+            (layer.fused or (not self.training and layer.distance_mode == QuantizeDistance.L2)) and not layer.needs_kmeans()
+            for layer in self.layers)
 
     def effective_codebooks(self) -> Tensor:
         """[L, K, D] stack of out_proj(embedding.weight) (autograd-tracked)."""
@@ -270,7 +275,7 @@ class HRqVae(nn.Module, _HubMixin):
         """All L levels -> (emb_out [L, N, D], residuals [L, N, D], ids [N, L], loss [N]).  One fused launch when
         possible, otherwise the level-by-level loop of the reference (first call with k-means init, Gumbel)."""
         if self._can_fuse():
-            mode = self.layers[0].forward_mode.value
+            mode = self.layers[0].forward_mode.value if self.layers[0].fused else QuantizeForwardMode.STE.value
             emb, res, ids, loss, _ll = ops.rq_apply(encoded_x, self.effective_codebooks(), mode, self.training,
                                                     self.commitment_weight, algo=self.layers[0].algo)
             if self.training and mode == QuantizeForwardMode.ROTATION_TRICK.value and encoded_x.shape[0] == 1:
