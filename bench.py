@@ -311,6 +311,8 @@ def run_native(args):
                               hbm_gbs=BYTES_ITEM * n / (step_ms * 1e-3) / 1e9),
                     kernels=kernels)
 
+    train_dp = run_train_dp(rank, world, dev) if not args.no_sweep else None
+
     sweep = None
     if rank == 0 and world == 1 and not args.no_sweep:
         del x_host
@@ -336,12 +338,125 @@ def run_native(args):
                     gpu_launches=(2 * n_chunks + 1) * args.steps, roofline=roofline, cpu_baseline=cpu, clocks=clocks, impl="native")
         if sweep is not None:
             line["sweep"] = sweep
+        if train_dp is not None:
+            line["train_dp"] = train_dp
         OUT.emit(json.dumps(line))
     if world > 1:
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)   # (tearing NCCL down was seen to hang on 2 x B200 with NCCL 2.28.9; nothing is pending here)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# C3: KuaiRand-shaped data-parallel training (k-means codebook init, tag heads, uniqueness loss, ONE flat gradient exchange)
+# ------------------------------------------------------------------------------------------------------------------
+def run_train_dp(rank, world, dev):
+    """BASELINE.json configs[2] through the module API: HRqVae.forward + backward on this rank's own batches (the
+    reference's per-rank sampling, train_hidvae.py:213,233), the 29 MB flat gradient all-reduce of
+    hidvae_b200.dist.FlatGradAllReduce (what DDP does inside accelerator.backward, train_hidvae.py:709) and the AdamW
+    step.  Codebooks come from the sharded k-means init (init/kmeans.py through Kmeans(process_group=...)).  Before
+    timing, hv_peer_allreduce and NCCL are run on the same buffer and compared.  Weak scaling: per-rank batch fixed."""
+    import torch.distributed as dist
+    from data.schemas import TaggedSeqBatch
+    from hidvae_b200 import dist as hv_dist
+    from modules.h_rqvae import HRqVae
+    from modules.quantize import QuantizeForwardMode
+    from train_hidvae import init_codebooks
+    import numpy as np
+
+    counts = [37, 168, 353]                                   # configs/h_rqvae_kuairand.gin:32
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = HRqVae(input_dim=768, embed_dim=32, hidden_dims=[512, 256, 128], codebook_size=256, codebook_kmeans_init=True,
+                   codebook_normalize=True, codebook_mode=QuantizeForwardMode.ROTATION_TRICK, n_layers=3, n_cat_features=0,
+                   commitment_weight=0.5, tag_class_counts=counts, tag_embed_dim=768, sem_id_uniqueness_weight=0.5,
+                   sem_id_uniqueness_margin=0.5).to(dev).train()
+    hv_dist.broadcast_parameters(model)
+    n_items = 32768                                            # per rank (the reference does not state KuaiRand's item count)
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    x = F.normalize(torch.randn(n_items, 768, generator=g, device=dev), dim=-1)
+    tags_emb = torch.randn(n_items, 3, 768, generator=g, device=dev)
+    tags_idx = torch.stack([torch.randint(0, c, (n_items,), generator=g, device=dev) for c in counts], dim=1)
+    tags_idx[torch.rand(n_items, 3, generator=g, device=dev) < 0.05] = -1
+    res = dict(model="KuaiRand-shaped HiD-VAE (7.24 M parameters, tag heads, k-means init, uniqueness loss)", items_per_rank=n_items)
+
+    # sharded k-means codebook init: min(20000, N) rows of the GLOBAL matrix, this rank's share of them
+    lo, hi = hv_dist.shard_range(20000, rank, world)
+    t0 = time.perf_counter()
+    init_codebooks(model, x[: hi - lo], process_group=dist.group.WORLD if world > 1 else None)
+    torch.cuda.synchronize()
+    res["kmeans_init_s"] = time.perf_counter() - t0
+    if world > 1:   # every rank must hold the same codebooks afterwards (the reference's ranks silently diverge)
+        cb = torch.stack([l.embedding.weight.detach() for l in model.layers])
+        ref = cb.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([float(torch.equal(cb, ref))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        res["codebooks_identical_on_all_ranks"] = bool(same.item())
+
+    grads = hv_dist.FlatGradAllReduce(model.parameters())
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+    res["flat_gradient_bytes"] = grads.flat.numel() * 4
+
+    if world > 1:   # the one-kernel peer-memory exchange against NCCL on the same data
+        try:
+            cb_n = sum(l.embedding.weight.numel() for l in model.layers)
+            peer = hv_dist.PeerAllReduce(cb_n, dev)
+            a = torch.randn(cb_n, generator=g, device=dev)
+            b = a.clone()
+            for _ in range(3):                                  # repeated calls exercise the flag parities
+                a2, b2 = a.clone(), b.clone()
+                peer(a2)
+                dist.all_reduce(b2)
+                ok = torch.allclose(a2, b2, rtol=1e-6, atol=1e-6)
+            peer.check()                                        # no call gave up waiting for a rank
+            okt = torch.tensor([float(ok)], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            res["allreduce_checked"] = bool(okt.item())
+            res["allreduce_check"] = "hv_peer_allreduce == NCCL all_reduce on the same 24,576-float buffer, 3 consecutive calls, every rank"
+        except Exception as e:  # noqa: BLE001
+            res["allreduce_checked"] = False
+            res["allreduce_check"] = f"peer-memory exchange unavailable: {type(e).__name__}: {e}"
+
+    for bs in (128, 8192):
+        def step():
+            idx = torch.randint(0, n_items, (bs,), device=dev, generator=g)
+            batch = TaggedSeqBatch(None, None, None, x[idx], None, None, tags_emb[idx], tags_idx[idx])
+            grads.zero()
+            out = model(batch, gumbel_t=0.2)
+            out.loss.backward()
+            grads.all_reduce()
+            opt.step()
+            return out.loss
+
+        for _ in range(5):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        reps = 30
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            loss = step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # the exchange alone (NCCL, 29 MB) on the same buffer
+        ar_ms = None
+        if world > 1:
+            a.record()
+            for _ in range(20):
+                dist.all_reduce(grads.flat)
+            b.record()
+            torch.cuda.synchronize()
+            ar_ms = a.elapsed_time(b) / 20
+        res[f"batch{bs}_per_rank"] = dict(ms_per_step=float(ms.item()), items_per_s=world * bs / (float(ms.item()) * 1e-3),
+                                           flat_allreduce_ms=ar_ms, loss=float(loss.detach()))
+    return res
 
 
 # ------------------------------------------------------------------------------------------------------------------

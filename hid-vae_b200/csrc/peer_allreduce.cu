@@ -8,9 +8,11 @@
 //
 //   inbox (per rank, symmetric):  [2 parities][world source ranks][n floats]
 //   flags (per rank, symmetric):  [2 parities][world source ranks][n_chunks] uint32, zero before the first call
-//   seq   (per rank, private):    [n_chunks] uint32 call counters, zero before the first call
+//   seq   (per rank, private):    [n_chunks] uint32 call counters + 1 sticky status word, zero before the first call
 // The call number lives in device memory (each CTA bumps its own counter), so a CUDA graph can replay the launch.
 // Two parities are enough: a rank reaches call s + 2 only after every peer has flagged call s + 1, i.e. has left call s.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace hv {
@@ -29,7 +31,16 @@ struct PeerArgs {
   uint32_t* seq;
   int rank;
   int world;
+  unsigned long long timeout_ns;  // 0 = wait for ever
 };
+
+std::atomic<long long> g_timeout_ms{10000};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -70,11 +81,15 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(PeerArgs a
   // ---- wait for this chunk from every rank, then sum the slots in rank order ----
   if (threadIdx.x < a.world) {
     const uint32_t* flag = reinterpret_cast<const uint32_t*>(a.flag_ptrs[a.rank]) + (par * a.world + threadIdx.x) * n_chunks + chunk;
-    const long long t0 = clock64();
+    // A rank that never shows up must not hang the box -- and must not poison the context of the ranks that did show up
+    // either: after `timeout_ns` of wall time (%globaltimer: independent of the SM clock) the wait is abandoned, the sticky
+    // status word behind the call counters records who was missing, and the launch completes with a meaningless sum that
+    // the host side refuses (PeerAllReduce.check / hv_peer_allreduce_status).
+    const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(flag) != seq) {
-      if (clock64() - t0 > 20000000000LL) {  // ~10 s: a rank that never shows up must not hang the box
-        printf("hidvae_b200: peer all-reduce timed out (rank %d waits for rank %d, chunk %d, call %u)\n", a.rank, threadIdx.x, chunk, seq);
-        __trap();
+      if (a.timeout_ns != 0 && global_ns() - t0 > a.timeout_ns) {
+        atomicCAS(a.seq + n_chunks, 0u, 0x80000000u | (static_cast<uint32_t>(threadIdx.x) << 16) | (static_cast<uint32_t>(chunk) & 0xFFFFu));
+        break;
       }
     }
   }
@@ -97,6 +112,19 @@ extern "C" {
 
 int hv_peer_allreduce_chunks(int64_t n) { return n <= 0 ? 0 : static_cast<int>((n + hv::kChunkFloats - 1) / hv::kChunkFloats); }
 
+void hv_peer_allreduce_set_timeout_ms(int64_t ms) { hv::g_timeout_ms.store(ms); }
+
+int hv_peer_allreduce_status(uint32_t status_word, int* missing_rank, int* chunk) {
+  if (missing_rank) *missing_rank = (status_word >> 16) & 0x7FFF;
+  if (chunk) *chunk = status_word & 0xFFFF;
+  if (status_word & 0x80000000u) {
+    hv::set_error("hv_peer_allreduce: timed out waiting for rank %u (chunk %u): the result of that call is invalid",
+                  (status_word >> 16) & 0x7FFFu, status_word & 0xFFFFu);
+    return HV_ERR_CUDA;
+  }
+  return HV_OK;
+}
+
 int hv_peer_allreduce(const float* src, float* dst, int64_t n, const uint64_t* inbox_ptrs, const uint64_t* flag_ptrs,
                       uint32_t* seq, int rank, int world, void* stream) {
   using namespace hv;
@@ -112,7 +140,8 @@ int hv_peer_allreduce(const float* src, float* dst, int64_t n, const uint64_t* i
     set_error("hv_peer_allreduce: src and dst must be 16-byte aligned");
     return HV_ERR_MISALIGNED;
   }
-  PeerArgs a{src, dst, n, inbox_ptrs, flag_ptrs, seq, rank, world};
+  const long long ms = g_timeout_ms.load();
+  PeerArgs a{src, dst, n, inbox_ptrs, flag_ptrs, seq, rank, world, ms > 0 ? static_cast<unsigned long long>(ms) * 1000000ull : 0ull};
   peer_allreduce_kernel<<<hv_peer_allreduce_chunks(n), kPeerThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   HV_CUDA_CHECK(cudaGetLastError());
   return HV_OK;

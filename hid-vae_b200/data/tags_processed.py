@@ -7,6 +7,7 @@ torch_geometric, polars: out of scope here and unavailable offline).  This ItemD
   * a seeded synthetic catalogue of the dataset's shape, resident on the device so that the
     training loop never waits on host memory.
 """
+import logging
 import os
 from enum import Enum
 from typing import Optional, Sequence
@@ -38,18 +39,29 @@ SYNTHETIC_SHAPES = {
 
 
 class ItemData(Dataset):
+    """Item catalogue with the reference's batch schema (data/tags_processed.py:44-278).
+
+    The processed catalogue `<root>/processed/items.pt` is loaded when it exists -- `force_process` never discards it
+    (re-processing the raw downloads is outside this repo: it needs polars / torch_geometric / an LLM service).  A seeded
+    SYNTHETIC catalogue of the same shape is built only when the caller opts in (`synthetic=True`, or an explicit
+    `n_items`); otherwise a missing file raises, so that a shipped gin config can never silently train on noise."""
+
     def __init__(self, root: str, *args, force_process: bool = False, dataset: RecDataset = RecDataset.ML_1M,
                  train_test_split: str = "all", n_items: Optional[int] = None, input_dim: int = 768,
                  tag_embed_dim: int = 768, tag_class_counts: Optional[Sequence[int]] = None, seed: int = 0,
-                 device: Optional[torch.device] = None, **kwargs) -> None:
+                 device: Optional[torch.device] = None, synthetic: Optional[bool] = None, **kwargs) -> None:
         shape = SYNTHETIC_SHAPES[dataset]
         path = os.path.join(root, "processed", "items.pt") if root else None
-        if path and os.path.isfile(path) and not force_process:
+        have_file = bool(path) and os.path.isfile(path)
+        if have_file and not synthetic:
+            if force_process:
+                logging.getLogger(__name__).warning(
+                    "force_process=True: raw re-processing is not part of this repo; loading the processed catalogue %s", path)
             blob = torch.load(path, map_location="cpu")
-            x, tags_emb, tags_indices = blob["x"][:, :768], blob.get("tags_emb"), blob.get("tags_indices")
+            x, tags_emb, tags_indices = blob["x"][:, :input_dim], blob.get("tags_emb"), blob.get("tags_indices")
             is_train = blob.get("is_train")
             self.synthetic = False
-        else:
+        elif synthetic or (synthetic is None and n_items is not None):
             n = n_items or shape["n_items"]
             counts = list(tag_class_counts or shape["tag_class_counts"])
             g = torch.Generator().manual_seed(seed)
@@ -59,6 +71,10 @@ class ItemData(Dataset):
             tags_indices[torch.rand(n, len(counts), generator=g) < 0.05] = -1   # 5 % missing tags
             is_train = torch.rand(n, generator=g) > 0.05                          # 95 / 5 split (tags_amazon.py:413)
             self.synthetic = True
+        else:
+            raise FileNotFoundError(
+                f"processed catalogue {path!r} not found.  Pass synthetic=True (gin: train.synthetic_data = True) or an "
+                "explicit n_items (train.synthetic_items) to build a seeded synthetic catalogue of the same shape.")
         if is_train is None:
             is_train = torch.rand(x.shape[0], generator=torch.Generator().manual_seed(42)) > 0.05
         keep = {"train": is_train, "eval": ~is_train, "all": torch.ones_like(is_train)}[train_test_split]

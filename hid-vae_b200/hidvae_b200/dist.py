@@ -30,7 +30,9 @@ def world_size(group=None) -> int:
 
 class FlatGradAllReduce:
     """Gives every parameter a `.grad` that is a view into one flat fp32 buffer, so that autograd accumulates
-    straight into it and the data-parallel exchange is a single collective with no packing copies."""
+    straight into it and the data-parallel exchange is a single collective with no packing copies.
+    Every parameter passed in therefore has a (possibly zero) gradient on every step: freeze parameters that cannot
+    receive one (`requires_grad_(False)`) so that they stay out of the buffer and the optimizer leaves them alone."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group=None, average: bool = True) -> None:
         self.params = [p for p in params if p.requires_grad]
@@ -77,6 +79,16 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> N
             dist.broadcast(t.data, src=src, group=group)
 
 
+def broadcast_buffers(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Rank `src`'s buffers (BatchNorm running statistics) to every rank -- DDP does this before every forward; here it
+    runs before evaluation and checkpointing, the two places where the buffers are read."""
+    if world_size(group) == 1:
+        return
+    for t in module.buffers():
+        if t is not None and t.is_floating_point():
+            dist.broadcast(t.data, src=src, group=group)
+
+
 def shard_range(n: int, rank: int, world: int) -> tuple:
     """Contiguous [lo, hi) of `n` items owned by `rank` (bulk semantic-ID assignment shards by items)."""
     per = (n + world - 1) // world
@@ -89,7 +101,12 @@ class PeerAllReduce:
     the inboxes in rank order, so all ranks end with bit-identical results.  For the latency-bound exchanges of the
     quantiser (98 KB of codebook gradient per step); large buffers belong to NCCL (`FlatGradAllReduce`).
     The inboxes and flags are a symmetric allocation (torch.distributed._symmetric_memory: CUDA peer mappings between the
-    processes of one node).  No fallback: a node without peer access fails in the constructor."""
+    processes of one node).  No fallback: a node without peer access fails in the constructor.
+
+    Ordering: consecutive calls on one instance must not overlap (the two-parity inbox reuse relies on it).  Calls made on
+    different streams are therefore chained with an event; inside a CUDA-graph capture the caller keeps them on one
+    stream.  A rank that never arrives does not trap the kernel: after `timeout_ms` the call completes with an invalid
+    result and `check()` (a host synchronisation) raises, naming the missing rank."""
 
     def __init__(self, numel: int, device, group=None) -> None:
         import torch.distributed._symmetric_memory as symm_mem
@@ -107,7 +124,9 @@ class PeerAllReduce:
         h_inbox, h_flags = symm_mem.rendezvous(self.inbox, name), symm_mem.rendezvous(self.flags, name)
         self.inbox_ptrs = torch.tensor([int(p) for p in h_inbox.buffer_ptrs], dtype=torch.int64, device=device)
         self.flag_ptrs = torch.tensor([int(p) for p in h_flags.buffer_ptrs], dtype=torch.int64, device=device)
-        self.seq = torch.zeros(n_chunks, dtype=torch.int32, device=device)
+        self.n_chunks = n_chunks
+        self.seq = torch.zeros(n_chunks + 1, dtype=torch.int32, device=device)   # call counters + sticky status word
+        self._last = None
         torch.cuda.synchronize(device)
         dist.barrier(self.group)  # every rank's flags are zero before anybody pushes
 
@@ -116,6 +135,26 @@ class PeerAllReduce:
         if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != self.n:
             raise ValueError(f"PeerAllReduce: expected a contiguous fp32 tensor of {self.n} elements")
         with torch.cuda.device(t.device):
+            stream = torch.cuda.current_stream(t.device)
+            capturing = torch.cuda.is_current_stream_capturing()
+            if self._last is not None and not capturing:
+                stream.wait_event(self._last)      # the previous call (possibly on another stream) has left the inboxes
             check(lib.hv_peer_allreduce(t.data_ptr(), t.data_ptr(), self.n, self.inbox_ptrs.data_ptr(), self.flag_ptrs.data_ptr(),
-                                        self.seq.data_ptr(), self.rank, self.world, torch.cuda.current_stream(t.device).cuda_stream))
+                                        self.seq.data_ptr(), self.rank, self.world, stream.cuda_stream))
+            if not capturing:
+                self._last = torch.cuda.Event()
+                self._last.record(stream)
         return t
+
+    @staticmethod
+    def set_timeout_ms(ms: int) -> None:
+        from hidvae_b200._lib import lib
+        lib.hv_peer_allreduce_set_timeout_ms(int(ms))
+
+    def check(self) -> None:
+        """Host synchronisation: raises HidvaeError if any call so far gave up waiting for a rank."""
+        import ctypes
+
+        from hidvae_b200._lib import check, lib
+        word = int(self.seq[self.n_chunks].item()) & 0xFFFFFFFF
+        check(lib.hv_peer_allreduce_status(ctypes.c_uint32(word), None, None))

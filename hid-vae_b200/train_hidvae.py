@@ -137,7 +137,9 @@ def train(
     use_interleaved_ids: bool = False,
     # -- additions (not in the reference): all optional ---------------------------------------------------------
     log_every=100,
-    synthetic_items=None,      # override the synthetic catalogue size
+    synthetic_items=None,      # opt in to a seeded synthetic catalogue of this many items
+    synthetic_data=None,       # True: opt in to the synthetic catalogue at the dataset's own size; a missing
+                               # `<dataset_folder>/processed/items.pt` raises unless one of the two is given
     seed=0,
     uniqueness_as_reference=True,
 ):
@@ -160,11 +162,17 @@ def train(
         logger.info("Training parameters: %s", {k: v for k, v in locals().items() if k not in ("logger",)})
 
     data_kw = dict(root=dataset_folder, dataset=dataset, force_process=force_dataset_process, n_items=synthetic_items,
-                   input_dim=vae_input_dim, tag_embed_dim=tag_embed_dim, tag_class_counts=tag_class_counts, device=device)
+                   input_dim=vae_input_dim, tag_embed_dim=tag_embed_dim, tag_class_counts=tag_class_counts, device=device,
+                   synthetic=synthetic_data)
     train_dataset = ItemData(train_test_split="train" if do_eval else "all", **data_kw)
     eval_dataset = ItemData(train_test_split="eval", **data_kw) if do_eval else None
     index_dataset = ItemData(train_test_split="all", **data_kw) if do_eval else train_dataset
     n_train = len(train_dataset)
+    if is_main and train_dataset.synthetic:
+        logger.warning("=" * 100)
+        logger.warning("TRAINING ON A SEEDED SYNTHETIC CATALOGUE (%d items): no processed dataset was loaded from %s. "
+                       "Losses, accuracies and checkpoints of this run say nothing about the real data.", n_train, dataset_folder)
+        logger.warning("=" * 100)
 
     has_tags = getattr(train_dataset, "has_tags", False)
     if not has_tags:
@@ -212,8 +220,19 @@ def train(
         optimizer.load_state_dict(state["optimizer"])
         start_iter = state["iter"] + 1
 
+    if not has_tags:
+        # no tag supervision: the tag heads receive no gradient.  The reference's optimizer skips parameters whose grad is
+        # None; freezing them keeps them out of the flat gradient buffer, so AdamW applies no weight decay to them either.
+        for p in list(model.tag_predictors.parameters()) + list(model.tag_projectors.parameters()):
+            p.requires_grad_(False)
     hv_dist.broadcast_parameters(model)                       # what DDP does in accelerator.prepare (:630)
     grads = hv_dist.FlatGradAllReduce(model.parameters())     # one flat buffer, one collective per step
+    # Batch-size semantics: every rank draws `batch_size` items per micro-step (global batch = world * batch_size), which
+    # is what the reference does in effect -- its dataloader is wrapped in cycle() before accelerator.prepare, so
+    # `split_batches` cannot shard it.  `split_batches` is accepted and ignored for that reason.
+    # fp16 autocast needs loss scaling (Accelerate(mixed_precision="fp16") applies a GradScaler, train_hidvae.py:186-189)
+    use_fp16 = bool(amp) and mixed_precision_type == "fp16"
+    scaler = torch.amp.GradScaler("cuda", enabled=use_fp16)
 
     scheduler = None
     if use_lr_scheduler:
@@ -253,8 +272,9 @@ def train(
     for it in range(start_iter, start_iter + 1 + iterations):
         model.train()
         if it == 0 and use_kmeans_init and pretrained_hrqvae_path is None:
-            n_init = min(20000, n_train)
-            init_codebooks(model, train_dataset[torch.arange(n_init, device=device)].x.float(),
+            n_init = min(20000, n_train)                          # (train_hidvae.py:693); every rank contributes its share
+            lo_i, hi_i = hv_dist.shard_range(n_init, rank, world)
+            init_codebooks(model, train_dataset[torch.arange(lo_i, hi_i, device=device)].x.float(),
                            process_group=torch.distributed.group.WORLD if world > 1 else None)
             if is_main:
                 logger.info("K-means initialization complete")
@@ -265,9 +285,11 @@ def train(
             batch = train_dataset[torch.randint(0, n_train, (batch_size,), device=device, generator=gen)]
             with torch.autocast("cuda", dtype=torch.float16 if mixed_precision_type == "fp16" else torch.bfloat16, enabled=bool(amp)):
                 out = model(batch, gumbel_t=t)
-            (out.loss / gradient_accumulate_every).backward()
-        grads.all_reduce()
-        optimizer.step()
+            scaler.scale(out.loss / gradient_accumulate_every).backward()
+        grads.all_reduce()                # (scaled) gradients first: every rank then sees the same inf / nan verdict
+        scaler.unscale_(optimizer)
+        scaler.step(optimizer)
+        scaler.update()
         if scheduler is not None:
             scheduler.step()
 
@@ -288,6 +310,7 @@ def train(
                         + f"items/s: {rate:.0f}")
 
         if do_eval and ((it + 1) % eval_every == 0 or it + 1 == iterations):
+            hv_dist.broadcast_buffers(model)   # BatchNorm running statistics: rank 0's, as DDP broadcasts buffers
             ev = evaluate(model, tokenizer, eval_dataset, index_dataset, batch_size, t, vae_n_layers, vae_codebook_size,
                           rank, world)
             if is_main:

@@ -180,10 +180,18 @@ int hv_encoder_forward(const float* x, int64_t n, int n_layers, const int* dims,
  *   n           floats, multiple of 4
  *   inbox_ptrs  device array [world] of the ranks' inbox bases as mapped in THIS process (symmetric allocation of
  *               2 * world * n floats per rank); flag_ptrs likewise for 2 * world * hv_peer_allreduce_chunks(n) uint32 flags
- *               (zero before the first call); seq: hv_peer_allreduce_chunks(n) private uint32 counters (zero before the
- *               first call).  Every rank must make the same sequence of calls.  CUDA-graph capturable.
+ *               (zero before the first call); seq: hv_peer_allreduce_chunks(n) + 1 private uint32 words (zero before the
+ *               first call): the call counters and one sticky STATUS word.  Every rank must make the same sequence of
+ *               calls, and consecutive calls on one set of inboxes must be ordered (one stream, or an event between them).
+ *               CUDA-graph capturable.
+ * A rank that does not show up within the timeout (default 10 s of wall time; hv_peer_allreduce_set_timeout_ms, 0 = wait for
+ * ever) does not trap the kernel: the wait is abandoned, the status word (seq[chunks]) is set and the call's result is
+ * invalid.  The caller copies that word to the host when it synchronises and passes it to hv_peer_allreduce_status
+ * (HV_OK, or HV_ERR_CUDA with the missing rank / chunk).
  */
 int hv_peer_allreduce_chunks(int64_t n);
+void hv_peer_allreduce_set_timeout_ms(int64_t ms);
+int hv_peer_allreduce_status(uint32_t status_word, int* missing_rank, int* chunk);
 int hv_peer_allreduce(const float* src, float* dst, int64_t n, const uint64_t* inbox_ptrs, const uint64_t* flag_ptrs,
                       uint32_t* seq, int rank, int world, void* stream);
 

@@ -143,3 +143,23 @@ def test_peer_allreduce_two_gpus():
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["ok"] is True
+
+
+def test_data_parallel_paths_on_nccl_two_gpus():
+    """Sharded k-means == single-process k-means, the flat gradient all-reduce, item-sharded bulk assignment + gather and
+    the trainer under torchrun on two GPUs over NCCL (tools/check_dp_nccl.py).  Needs two GPUs on the box."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29549", os.path.join(root, "tools", "check_dp_nccl.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, (out.stdout[-1500:] + out.stderr[-2500:])
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["ok"] is True

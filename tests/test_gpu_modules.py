@@ -278,3 +278,43 @@ train.log_every = 10
     assert logs[-1]["rqvae"] < logs[0]["rqvae"] * 1.05
     assert 0.0 <= evals[-1]["sem_id_repetition_rate"] <= 1.0 and evals[-1]["codebook_usage_0"] > 0.3
     gin_lite.clear_config()
+
+
+def test_trainer_fp16_amp_uses_loss_scaling_and_refuses_silent_synthetic_data(mods, tmp_path):
+    """amp=True with the reference's default mixed_precision_type='fp16' (Accelerate applies a GradScaler there): the
+    encoder must receive non-zero, finite gradients and the run must stay finite.  And a missing processed catalogue
+    must raise unless synthetic data is asked for."""
+    from hidvae_b200 import gin_lite
+    import train_hidvae
+    base = """
+import modules.quantize
+train.iterations = 8
+train.batch_size = 128
+train.vae_input_dim = 768
+train.vae_n_cat_feats = 0
+train.vae_hidden_dims = [128, 64]
+train.vae_embed_dim = 32
+train.vae_codebook_size = 64
+train.vae_codebook_normalize = True
+train.vae_codebook_mode = %modules.quantize.QuantizeForwardMode.ROTATION_TRICK
+train.dataset = %data.tags_processed.RecDataset.AMAZON
+train.tag_class_counts = [8, 16, 32]
+train.use_kmeans_init = False
+train.do_eval = False
+train.log_every = 2
+train.amp = True
+train.mixed_precision_type = "fp16"
+"""
+    gin_lite.clear_config()
+    gin_lite.parse_config(base)
+    with pytest.raises(FileNotFoundError):
+        train_hidvae.train(save_dir_root=str(tmp_path), dataset_folder=str(tmp_path / "nothing_here"))
+    gin_lite.clear_config()
+    gin_lite.parse_config(base + "train.synthetic_data = True\ntrain.synthetic_items = 2000\n")
+    before = None
+    res = train_hidvae.train(save_dir_root=str(tmp_path), dataset_folder="")
+    logs = [h for h in res["history"] if "eval" not in h]
+    assert logs and all(np.isfinite(h["loss"]) for h in logs)
+    enc_w = res["model"].encoder.mlp[0].weight
+    assert enc_w.grad is not None and bool(torch.isfinite(enc_w.grad).all()) and float(enc_w.grad.abs().max()) > 0.0
+    gin_lite.clear_config()
