@@ -5,7 +5,11 @@
 // (B^2/2 eight-byte compares, no HBM traffic beyond the ids), and only key-equal pairs -- verified element by
 // element, so the hash never decides -- touch the feature rows.  Sums are kept in double, one atomic per CTA.
 // No host-side data-dependent control flow: the call is CUDA-graph capturable.
+// Beyond a few thousand rows the B^2/2 sweep is replaced by a SORT: rows are key-sorted by the hash of their tuple (stable
+// radix sort, sort.cuh), identical tuples then sit in one run in ascending row order, and a thread per sorted position
+// walks the rest of its run -- O(B + pairs) instead of O(B^2) (the loss itself is a sum over pairs of identical tuples).
 #include "common.cuh"
+#include "sort.cuh"
 
 namespace hv {
 namespace {
@@ -129,6 +133,77 @@ __global__ void __launch_bounds__(kTile) uniq_kernel(UniqArgs a, double* __restr
   }
 }
 
+// ---- sorted form ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile) uniq_keys_kernel(UniqArgs a, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kTile + threadIdx.x;
+  if (i < a.rows) {
+    keys[i] = row_key(a, i);
+    vals[i] = static_cast<uint32_t>(i);
+  }
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kTile) uniq_sorted_kernel(UniqArgs a, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ order,
+                                                            double* __restrict__ stats_out, const double* __restrict__ stats_in, float weight,
+                                                            const float* __restrict__ g_out, float* __restrict__ g_feats) {
+  __shared__ double s_scratch[kTile / 32];
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * kTile + threadIdx.x;
+  float coef = 0.f;
+  if (BACKWARD) {
+    const double pairs = stats_in[1];
+    coef = pairs > 0.0 ? static_cast<float>(static_cast<double>(g_out[0]) * weight / pairs) : 0.f;
+  }
+  double hinge_sum = 0.0, pair_count = 0.0, has_later = 0.0;
+  if (p < a.rows) {
+    const uint64_t my_key = keys[p];
+    const int64_t i = order[p];
+    for (int64_t q = p + 1; q < a.rows && keys[q] == my_key; ++q) {
+      const int64_t j = order[q];  // (stable sort: j > i)
+      if (!same_tuple(a, i, j)) continue;
+      float inv_i, inv_j;
+      const float cs = pair_cos(a, i, j, &inv_i, &inv_j);
+      const float hinge = cs - a.margin;
+      if (!BACKWARD) {
+        has_later = 1.0;
+        pair_count += 1.0;
+        if (hinge > 0.f) hinge_sum += static_cast<double>(hinge);
+      } else if (hinge > 0.f && coef != 0.f) {
+        const float* fi = a.feats + i * a.d;
+        const float* fj = a.feats + j * a.d;
+        for (int c = 0; c < a.d; ++c) {
+          const float hi = fi[c] * inv_i, hj = fj[c] * inv_j;
+          atomicAdd(g_feats + i * a.d + c, coef * (hj - cs * hi) * inv_i);
+          atomicAdd(g_feats + j * a.d + c, coef * (hi - cs * hj) * inv_j);
+        }
+      }
+    }
+  }
+  if (!BACKWARD) {
+    const double t0 = block_sum<double>(hinge_sum, s_scratch);
+    const double t1 = block_sum<double>(pair_count, s_scratch);
+    const double t2 = block_sum<double>(has_later, s_scratch);
+    if (threadIdx.x == 0) {
+      if (t0 != 0.0) atomicAdd(stats_out + 0, t0);
+      if (t1 != 0.0) atomicAdd(stats_out + 1, t1);
+      if (t2 != 0.0) atomicAdd(stats_out + 2, t2);
+    }
+  }
+}
+
+constexpr int64_t kSortFromRows = 4096;  // below: the pairwise sweep is one small launch and wins
+
+template <bool BACKWARD>
+int launch_sorted(const UniqArgs& a, const SortBuffers& b, double* stats_out, const double* stats_in, float weight, const float* g_out,
+                  float* g_feats, cudaStream_t s) {
+  const unsigned grid = static_cast<unsigned>((a.rows + kTile - 1) / kTile);
+  uniq_keys_kernel<<<grid, kTile, 0, s>>>(a, b.keys_in, b.vals_in);
+  HV_CUDA_CHECK(cudaGetLastError());
+  if (int st = sort_pairs(b, a.rows, 64, s)) return st;
+  uniq_sorted_kernel<BACKWARD><<<grid, kTile, 0, s>>>(a, b.keys_out, b.vals_out, stats_out, stats_in, weight, g_out, g_feats);
+  HV_CUDA_CHECK(cudaGetLastError());
+  return HV_OK;
+}
+
 int check(const int64_t* ids, int64_t rows, int64_t width, const float* feats, int d, const char* who) {
   if (rows < 0 || width <= 0 || d < 0) {
     set_error("%s: bad shape rows=%lld width=%lld d=%d", who, (long long)rows, (long long)width, d);
@@ -145,7 +220,8 @@ int check(const int64_t* ids, int64_t rows, int64_t width, const float* feats, i
 }  // namespace hv
 
 extern "C" int hv_uniq_forward(const int64_t* ids, int64_t rows, int64_t width, int64_t row_stride, int64_t col_stride,
-                               const float* feats, int d, float margin, double* stats, void* stream) {
+                               const float* feats, int d, float margin, double* stats, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   using namespace hv;
   if (int st = check(ids, rows, width, feats, d, "hv_uniq_forward")) return st;
   if (!stats) {
@@ -156,6 +232,9 @@ extern "C" int hv_uniq_forward(const int64_t* ids, int64_t rows, int64_t width, 
   HV_CUDA_CHECK(cudaMemsetAsync(stats, 0, 3 * sizeof(double), s));
   if (rows == 0) return HV_OK;
   UniqArgs a{ids, rows, width, row_stride, col_stride, feats, d, margin};
+  SortBuffers bufs;
+  if (rows >= kSortFromRows && sort_carve(workspace, workspace_bytes, rows, &bufs))
+    return launch_sorted<false>(a, bufs, stats, nullptr, 0.f, nullptr, nullptr, s);
   const unsigned grid = static_cast<unsigned>((rows + kTile - 1) / kTile);
   uniq_kernel<false><<<grid, kTile, 0, s>>>(a, stats, nullptr, 0.f, nullptr, nullptr);
   HV_CUDA_CHECK(cudaGetLastError());
@@ -164,7 +243,7 @@ extern "C" int hv_uniq_forward(const int64_t* ids, int64_t rows, int64_t width, 
 
 extern "C" int hv_uniq_backward(const int64_t* ids, int64_t rows, int64_t width, int64_t row_stride, int64_t col_stride,
                                 const float* feats, int d, float margin, float weight, const double* stats,
-                                const float* g_out, float* g_feats, void* stream) {
+                                const float* g_out, float* g_feats, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace hv;
   if (int st = check(ids, rows, width, feats, d, "hv_uniq_backward")) return st;
   if (!stats || !g_out || (rows > 0 && !g_feats)) {
@@ -173,6 +252,9 @@ extern "C" int hv_uniq_backward(const int64_t* ids, int64_t rows, int64_t width,
   }
   if (rows == 0) return HV_OK;
   UniqArgs a{ids, rows, width, row_stride, col_stride, feats, d, margin};
+  SortBuffers bufs;
+  if (rows >= kSortFromRows && sort_carve(workspace, workspace_bytes, rows, &bufs))
+    return launch_sorted<true>(a, bufs, nullptr, stats, weight, g_out, g_feats, static_cast<cudaStream_t>(stream));
   const unsigned grid = static_cast<unsigned>((rows + kTile - 1) / kTile);
   uniq_kernel<true><<<grid, kTile, 0, static_cast<cudaStream_t>(stream)>>>(a, nullptr, stats, weight, g_out, g_feats);
   HV_CUDA_CHECK(cudaGetLastError());

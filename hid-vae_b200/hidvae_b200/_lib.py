@@ -41,13 +41,14 @@ SIGNATURES = {
     "hv_rq_backward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hv_sort_workspace_bytes": (c_size_t, [c_int64]),
     "hv_kmeans_accumulate": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                     c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_size_t, c_void_p]),
     "hv_kmeans_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hv_uniq_forward": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_float,
-                                c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_size_t, c_void_p]),
     "hv_uniq_backward": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_float, c_float,
-                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hv_encoder_workspace_bytes": (c_size_t, [c_int, POINTER(c_int)]),
     "hv_encoder_pack_weights": (c_int, [POINTER(c_void_p), c_int, POINTER(c_int), c_void_p, c_size_t, c_void_p]),
     "hv_encoder_forward": (c_int, [c_void_p, c_int64, c_int, POINTER(c_int), c_void_p, c_size_t, c_int, c_int, c_void_p,

@@ -158,32 +158,41 @@ def rq_backward(x: Tensor, codebooks: Tensor, ids: Tensor, mode: int, training: 
 class RqFunction(torch.autograd.Function):
     """Differentiable fused residual quantiser.
 
-    forward(x [N, D], codebooks [L, K, D], mode, training, beta, algo)
+    forward(x [N, D], codebooks [L, K, D], mode, training, beta, algo, want_residuals, want_level_loss)
         -> emb_out [L, N, D], residuals [L, N, D] (not differentiable), ids [N, L], loss [N], level_loss [L, N]
+        (residuals / level_loss are empty placeholders when not wanted: 4DL + 4L bytes per item less to write)
     backward implements the recursion of SURVEY.md section 8a (autograd of modules/quantize.py:131-148 and
     modules/h_rqvae.py:552); the forward chain is recomputed, only x, codebooks and ids are saved."""
 
     @staticmethod
-    def forward(ctx, x, codebooks, mode, training, beta, algo):
-        out = rq_forward(x, codebooks, mode, training, beta, want_emb=True, want_residuals=True, want_loss=True,
-                         want_level_loss=True, algo=algo)
+    def forward(ctx, x, codebooks, mode, training, beta, algo, want_residuals=True, want_level_loss=True):
+        out = rq_forward(x, codebooks, mode, training, beta, want_emb=True, want_residuals=want_residuals, want_loss=True,
+                         want_level_loss=want_level_loss, algo=algo)
         ctx.save_for_backward(x, codebooks, out.ids)
         ctx.cfg = (int(mode), bool(training), float(beta))
-        ctx.mark_non_differentiable(out.ids, out.residuals)
-        return out.emb_out, out.residuals, out.ids, out.loss, out.level_loss
+        residuals = out.residuals if want_residuals else x.new_empty(0)
+        level_loss = out.level_loss if want_level_loss else x.new_empty(0)
+        ctx.want_level_loss = bool(want_level_loss)
+        ctx.mark_non_differentiable(out.ids, residuals)
+        return out.emb_out, residuals, out.ids, out.loss, level_loss
 
     @staticmethod
     def backward(ctx, g_emb, _g_res, _g_ids, g_loss, g_level_loss):
         x, codebooks, ids = ctx.saved_tensors
         mode, training, beta = ctx.cfg
-        g_x, g_cb = rq_backward(x, codebooks, ids, mode, training, beta, g_emb, g_loss, g_level_loss)
+        g_x, g_cb = rq_backward(x, codebooks, ids, mode, training, beta, g_emb, g_loss,
+                                g_level_loss if ctx.want_level_loss else None)
         return (g_x if ctx.needs_input_grad[0] else None, g_cb if ctx.needs_input_grad[1] else None,
-                None, None, None, None)
+                None, None, None, None, None, None)
 
 
-def rq_apply(x: Tensor, codebooks: Tensor, mode: int, training: bool, beta: float, algo="auto"):
-    """Autograd entry: returns (emb_out [L,N,D], residuals [L,N,D], ids [N,L], loss [N], level_loss [L,N])."""
-    return RqFunction.apply(x, codebooks, int(mode), bool(training), float(beta), algo)
+def rq_apply(x: Tensor, codebooks: Tensor, mode: int, training: bool, beta: float, algo="auto",
+             want_residuals: bool = True, want_level_loss: bool = True):
+    """Autograd entry: returns (emb_out [L,N,D], residuals [L,N,D], ids [N,L], loss [N], level_loss [L,N]); residuals /
+    level_loss come back as None when not wanted."""
+    emb, res, ids, loss, ll = RqFunction.apply(x, codebooks, int(mode), bool(training), float(beta), algo,
+                                               bool(want_residuals), bool(want_level_loss))
+    return emb, (res if want_residuals else None), ids, loss, (ll if want_level_loss else None)
 
 
 def rq_encode(x: Tensor, codebooks: Tensor, algo="auto", ids_out: Optional[Tensor] = None,
@@ -254,6 +263,12 @@ def kmeans_assign(x: Tensor, centroids: Tensor, exact_diff_form: bool = True) ->
     return rq_forward(x, centroids.unsqueeze(0), HV_MODE_STE, False, 0.0, algo=algo).ids.view(-1)
 
 
+def _sort_workspace(n: int, device) -> Optional[Tensor]:
+    """Scratch of the key sort behind the segmented k-means update and the sorted uniqueness pass (None for n == 0)."""
+    nbytes = int(lib.hv_sort_workspace_bytes(n))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes else None
+
+
 def kmeans_accumulate(x: Tensor, assign: Tensor, k: int, prev_assign: Optional[Tensor] = None):
     """Deterministic per-cluster sums [K, D], counts [K] and the number of changed assignments (0-d int64)."""
     _require_cuda(x, assign)
@@ -265,9 +280,11 @@ def kmeans_accumulate(x: Tensor, assign: Tensor, k: int, prev_assign: Optional[T
     assign = assign.contiguous()
     if prev_assign is not None:
         prev_assign = prev_assign.contiguous()
+    ws = _sort_workspace(n, x.device) if k * n > (1 << 24) else None
     with torch.cuda.device(x.device):
         check(lib.hv_kmeans_accumulate(x.data_ptr(), n, d, assign.data_ptr(), _ptr(prev_assign), k, sums.data_ptr(),
-                                       counts.data_ptr(), changed.data_ptr(), _stream(x)))
+                                       counts.data_ptr(), changed.data_ptr(), _ptr(ws), ws.numel() if ws is not None else 0,
+                                       _stream(x)))
     return sums, counts, changed
 
 
@@ -301,9 +318,10 @@ def uniq_stats(ids: Tensor, feats: Optional[Tensor], margin: float) -> Tensor:
         feats = _f32c(feats)
         d = feats.shape[1]
     stats = torch.empty((3,), dtype=torch.float64, device=ids.device)
+    ws = _sort_workspace(rows, ids.device) if rows >= 4096 else None
     with torch.cuda.device(ids.device):
         check(lib.hv_uniq_forward(ids.data_ptr(), rows, width, ids.stride(0), ids.stride(1), _ptr(feats), d,
-                                  float(margin), stats.data_ptr(), _stream(ids)))
+                                  float(margin), stats.data_ptr(), _ptr(ws), ws.numel() if ws is not None else 0, _stream(ids)))
     return stats
 
 
@@ -325,10 +343,11 @@ class UniqFunction(torch.autograd.Function):
         g_feats = torch.zeros_like(feats)
         g = g_out.contiguous().float().reshape(1)
         rows, width = ids.shape
+        ws = _sort_workspace(rows, feats.device) if rows >= 4096 else None
         with torch.cuda.device(feats.device):
             check(lib.hv_uniq_backward(ids.data_ptr(), rows, width, ids.stride(0), ids.stride(1), feats.data_ptr(),
                                        feats.shape[1], margin, weight, stats.data_ptr(), g.data_ptr(),
-                                       g_feats.data_ptr(), _stream(feats)))
+                                       g_feats.data_ptr(), _ptr(ws), ws.numel() if ws is not None else 0, _stream(feats)))
         return g_feats, None, None, None
 
 

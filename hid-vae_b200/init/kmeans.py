@@ -97,7 +97,13 @@ class Kmeans:
     def _update_centroids(self, x: Tensor) -> float:
         """One Lloyd iteration; returns max_c ||c_new - c_old||_2 (the quantity of init/kmeans.py:68)."""
         dist = self._dist()
-        new_assign = ops.kmeans_assign(x, self.centroids, exact_diff_form=True)
+        # Assignment = the fused distance + argmin kernel with one level.  Small problems use its exact-fp32 CUDA-core
+        # variant in the reference's difference form sum (x - c)^2 (init/kmeans.py:44-47: assignments then match the
+        # reference bit for bit); from K * N > 2^24 on (K = 4096 at 65,536 rows is 17 G multiply-adds) the tcgen05 variant
+        # takes over -- GEMM form, fp32-grade scores, same near-tie policy as the quantiser (a row may take the other of
+        # two centroids whose distances differ by < 1e-5 relative).  Both are deterministic functions of (x, centroids).
+        exact = self.k * x.shape[0] <= (1 << 24) or not ops.workspace_bytes(x.shape[1], self.k, 1)
+        new_assign = ops.kmeans_assign(x, self.centroids, exact_diff_form=exact)
         sums, counts, _changed = ops.kmeans_accumulate(x, new_assign, self.k, self.assignment)
         if dist is not None:
             dist.all_reduce(sums, group=self.process_group)

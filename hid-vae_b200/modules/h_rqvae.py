@@ -271,13 +271,15 @@ class HRqVae(nn.Module, _HubMixin):
         """[L, K, D] stack of out_proj(embedding.weight) (autograd-tracked)."""
         return torch.stack([layer.effective_codebook() for layer in self.layers])
 
-    def quantize_all_levels(self, encoded_x: Tensor, gumbel_t: float = 0.001):
+    def quantize_all_levels(self, encoded_x: Tensor, gumbel_t: float = 0.001, want_residuals: bool = True):
         """All L levels -> (emb_out [L, N, D], residuals [L, N, D], ids [N, L], loss [N]).  One fused launch when
-        possible, otherwise the level-by-level loop of the reference (first call with k-means init, Gumbel)."""
+        possible, otherwise the level-by-level loop of the reference (first call with k-means init, Gumbel).
+        `want_residuals=False` (the training step: HRqVae.forward never reads them) skips writing [L, N, D]."""
         if self._can_fuse():
             mode = self.layers[0].forward_mode.value if self.layers[0].fused else QuantizeForwardMode.STE.value
             emb, res, ids, loss, _ll = ops.rq_apply(encoded_x, self.effective_codebooks(), mode, self.training,
-                                                    self.commitment_weight, algo=self.layers[0].algo)
+                                                    self.commitment_weight, algo=self.layers[0].algo,
+                                                    want_residuals=want_residuals, want_level_loss=False)
             if self.training and mode == QuantizeForwardMode.ROTATION_TRICK.value and encoded_x.shape[0] == 1:
                 pass  # shapes stay [L, 1, D]; the per-level API reproduces the reference's squeeze, the fused one does not
             return emb, res, ids, loss
@@ -295,9 +297,10 @@ class HRqVae(nn.Module, _HubMixin):
         return torch.stack(embs), torch.stack(residuals), torch.stack(ids, dim=1), loss
 
     def get_semantic_ids(self, encoded_x: Tensor, tags_emb: Optional[Tensor] = None,
-                         tags_indices: Optional[Tensor] = None, gumbel_t: float = 0.001) -> HRqVaeOutput:
+                         tags_indices: Optional[Tensor] = None, gumbel_t: float = 0.001,
+                         _want_residuals: bool = True) -> HRqVaeOutput:
         dev = encoded_x.device
-        emb, residuals, sem_ids, quantize_loss = self.quantize_all_levels(encoded_x, gumbel_t)
+        emb, residuals, sem_ids, quantize_loss = self.quantize_all_levels(encoded_x, gumbel_t, want_residuals=_want_residuals)
 
         zero = lambda: torch.tensor(0.0, device=dev)
         align_total, pred_total, acc_total = zero(), zero(), zero()
@@ -316,7 +319,7 @@ class HRqVae(nn.Module, _HubMixin):
 
         return HRqVaeOutput(
             embeddings=emb.permute(1, 2, 0),          # [N, D, L] like rearrange(embs, "b h d -> h d b")
-            residuals=residuals.permute(1, 2, 0),
+            residuals=residuals.permute(1, 2, 0) if residuals is not None else None,
             sem_ids=sem_ids,                          # [N, L]
             quantize_loss=quantize_loss,
             tag_align_loss=align_total,
@@ -335,7 +338,7 @@ class HRqVae(nn.Module, _HubMixin):
             tags_emb = tags_emb.float()
 
         encoded = self.encode(x)
-        q = self.get_semantic_ids(encoded, tags_emb, tags_indices, gumbel_t)
+        q = self.get_semantic_ids(encoded, tags_emb, tags_indices, gumbel_t, _want_residuals=False)  # (:604 reads, never uses them)
 
         x_hat = self.decode(q.embeddings.sum(dim=-1))
         # reference :610 -- with n_cat_feats == 0 the slices are [:-0] (empty) and [-0:] (everything): identity

@@ -131,7 +131,8 @@ class Quantize(nn.Module):
             # eval semantics are mode-independent (emb_out = codebook[ids], reference :146-148)
             mode = self.forward_mode.value if self.fused else QuantizeForwardMode.STE.value
             emb, _res, ids, loss, _ll = ops.rq_apply(x, codebook.unsqueeze(0), mode, self.training,
-                                                     self.commitment_weight, algo=self.algo)
+                                                     self.commitment_weight, algo=self.algo,
+                                                     want_residuals=False, want_level_loss=False)
             emb_out = emb[0]
             if self.training and self.forward_mode == QuantizeForwardMode.ROTATION_TRICK and x.shape[0] == 1:
                 emb_out = emb_out.squeeze()  # the reference's transform ends in .squeeze() (quantize.py:45)

@@ -126,15 +126,20 @@ int hv_rq_backward(const float* x, int64_t n, int d, const float* codebooks, int
 
 /*
  * K-means codebook init (init/kmeans.py:43-61).  Assignment = hv_rq_forward with n_levels = 1 (ids only).
- * hv_kmeans_accumulate: deterministic per-cluster sums and counts of the assigned rows
+ * hv_kmeans_accumulate: deterministic (bit-reproducible) per-cluster sums and counts of the assigned rows
  *   sums [K, D] and counts [K] (float) are OVERWRITTEN; n_changed[0] (int64, may be NULL) receives the number
  *   of rows whose assignment differs from prev_assign (NULL = count every row).
+ *   workspace: optional hv_sort_workspace_bytes(n) bytes.  With it, large K * N take the SEGMENTED form: rows are
+ *   key-sorted by cluster (stable radix sort) and one warp per cluster adds its members in row order -- O(N), x read
+ *   once; without it (or for small shapes) one CTA per cluster scans the assignment vector.
  * hv_kmeans_finalize: centroid_c = sums_c / counts_c, or reseed_rows[c, :] when counts_c == 0 (kmeans.py:54-58);
  *   centroids [K, D] are updated in place; stats[0] = max_c ||new_c - old_c||_2 (kmeans.py:68), stats[1] =
  *   number of empty clusters.  Between the two calls a data-parallel caller all-reduces sums and counts.
  */
+size_t hv_sort_workspace_bytes(int64_t n);
 int hv_kmeans_accumulate(const float* x, int64_t n, int d, const int64_t* assign, const int64_t* prev_assign,
-                         int k, float* sums, float* counts, int64_t* n_changed, void* stream);
+                         int k, float* sums, float* counts, int64_t* n_changed, void* workspace, size_t workspace_bytes,
+                         void* stream);
 int hv_kmeans_finalize(const float* sums, const float* counts, const float* reseed_rows, int k, int d,
                        float* centroids, float* stats, void* stream);
 
@@ -146,12 +151,15 @@ int hv_kmeans_finalize(const float* sums, const float* counts, const float* rese
  *          stats is OVERWRITTEN.  loss = weight * stats[0] / stats[1] (0 when stats[1] == 0) is formed by the
  *          caller on the device; p_unique = (rows - stats[2]) / rows.
  * Backward: g_feats [rows, D] (caller zeroes) += g_out[0] * weight / stats[1] * d(sum)/d feats.
+ * workspace: optional hv_sort_workspace_bytes(rows) bytes.  With it, batches of >= 4096 rows are key-sorted by tuple and
+ *   only runs of identical tuples are walked (O(rows + pairs)); otherwise all pairs i < j are swept (O(rows^2)).
  */
 int hv_uniq_forward(const int64_t* ids, int64_t rows, int64_t width, int64_t row_stride, int64_t col_stride,
-                    const float* feats, int d, float margin, double* stats, void* stream);
+                    const float* feats, int d, float margin, double* stats, void* workspace, size_t workspace_bytes,
+                    void* stream);
 int hv_uniq_backward(const int64_t* ids, int64_t rows, int64_t width, int64_t row_stride, int64_t col_stride,
                      const float* feats, int d, float margin, float weight, const double* stats,
-                     const float* g_out, float* g_feats, void* stream);
+                     const float* g_out, float* g_feats, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Fused encoder MLP in front of the quantiser: z = [l2norm](W_L silu(... silu(W_1 x))) -- the bias-free Linear + SiLU

@@ -163,3 +163,80 @@ def test_data_parallel_paths_on_nccl_two_gpus():
     assert out.returncode == 0, (out.stdout[-1500:] + out.stderr[-2500:])
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["ok"] is True
+
+
+@pytest.mark.parametrize("n,d,k", [(70000, 32, 1024), (65536, 64, 4096), (40000, 16, 513)])
+def test_kmeans_segmented_update_large_k(ops, n, d, k):
+    """K * N beyond 2^24: the update sorts the rows by cluster and sums every segment in row order (hv_kmeans_accumulate
+    with the sort workspace).  Exact counts, sums equal to a float64 reference within fp32 summation error, bit-identical
+    from run to run, and the same sums (to fp32 round-off) as the scan form that small shapes use."""
+    from hidvae_b200 import _lib
+    x = unit_rows(n, d, 71).cuda()
+    g = torch.Generator().manual_seed(72)
+    assign = torch.randint(0, k, (n,), generator=g)
+    assign[assign == 7] = 8                                  # cluster 7 is empty
+    assign = assign.cuda()
+    prev = assign.clone()
+    prev[::5] = (prev[::5] + 3) % k
+    s1, c1, ch1 = ops.kmeans_accumulate(x, assign, k, prev)
+    s2, c2, _ = ops.kmeans_accumulate(x, assign, k, prev)
+    assert torch.equal(s1, s2) and torch.equal(c1, c2)
+    assert int(ch1) == int((prev != assign).sum())
+    ref_counts = torch.bincount(assign, minlength=k).float()
+    assert torch.equal(c1, ref_counts) and float(c1[7]) == 0.0 and float(s1[7].abs().max()) == 0.0
+    ref = torch.zeros(k, d, dtype=torch.float64, device="cuda").index_add_(0, assign, x.double())
+    torch.testing.assert_close(s1.double(), ref, rtol=1e-5, atol=1e-5)
+    # scan form (no workspace) on the same inputs through the raw C ABI
+    sums = torch.empty_like(s1)
+    counts = torch.empty_like(c1)
+    _lib.check(_lib.lib.hv_kmeans_accumulate(x.data_ptr(), n, d, assign.data_ptr(), None, k, sums.data_ptr(), counts.data_ptr(),
+                                             None, None, 0, torch.cuda.current_stream().cuda_stream))
+    torch.testing.assert_close(sums, s1, rtol=1e-5, atol=1e-5)
+    assert torch.equal(counts, c1)
+
+
+def test_kmeans_run_large_codebook_reaches_fixed_point(ops):
+    """Kmeans.run at the stress shape (K = 4096, D = 64, 65,536 rows): the segmented update is deterministic, so the Lloyd
+    loop reaches the reference's 1e-10 stop threshold; inertia must not increase from one update to the next."""
+    from init.kmeans import Kmeans
+    x = unit_rows(65536, 64, 5).cuda()
+    np.random.seed(3)
+    torch.manual_seed(3)
+    km = Kmeans(k=4096, max_iters=60)
+    out = km.run(x)
+    assert out.centroids.shape == (4096, 64) and out.assignment.shape == (65536,)
+    d_final = (x - out.centroids[out.assignment]).pow(2).sum()
+    np.random.seed(3)
+    torch.manual_seed(3)
+    short = Kmeans(k=4096, max_iters=2).run(x)
+    d_short = (x - short.centroids[short.assignment]).pow(2).sum()
+    assert float(d_final) <= float(d_short) * (1 + 1e-6)
+
+
+@pytest.mark.parametrize("b", [6000, 65536])
+def test_uniqueness_sorted_path_equals_pairwise_sweep(ops, b):
+    """>= 4096 rows take the sorted path (runs of identical tuples); it must give the pairwise sweep's statistics and
+    feature gradient (the sweep is the form verified against the reference golden and the oracle)."""
+    import ctypes
+    from hidvae_b200 import _lib
+    g = torch.Generator().manual_seed(81)
+    ids = torch.randint(0, 24, (b, 3), generator=g).cuda()
+    ids[100] = ids[4000]                                          # a pair far apart in row order
+    feats = torch.randn(b, 32, generator=g).cuda()
+    margin, weight = 0.05, 1.5
+    stream = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(int(_lib.lib.hv_sort_workspace_bytes(b)), dtype=torch.uint8, device="cuda")
+    res = {}
+    for name, (wp, wb) in {"sorted": (ws.data_ptr(), ws.numel()), "sweep": (None, 0)}.items():
+        stats = torch.empty(3, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib.hv_uniq_forward(ids.data_ptr(), b, 3, ids.stride(0), ids.stride(1), feats.data_ptr(), 32, margin,
+                                            stats.data_ptr(), wp, wb, stream))
+        gf = torch.zeros_like(feats)
+        gout = torch.ones(1, device="cuda")
+        _lib.check(_lib.lib.hv_uniq_backward(ids.data_ptr(), b, 3, ids.stride(0), ids.stride(1), feats.data_ptr(), 32, margin,
+                                             ctypes.c_float(weight), stats.data_ptr(), gout.data_ptr(), gf.data_ptr(), wp, wb, stream))
+        res[name] = (stats.cpu(), gf.cpu())
+    assert float(res["sorted"][0][1]) == float(res["sweep"][0][1]) > 0          # pairs
+    assert float(res["sorted"][0][2]) == float(res["sweep"][0][2])              # rows with a later twin
+    torch.testing.assert_close(res["sorted"][0][0], res["sweep"][0][0], rtol=1e-9, atol=1e-9)
+    torch.testing.assert_close(res["sorted"][1], res["sweep"][1], rtol=1e-4, atol=1e-7)

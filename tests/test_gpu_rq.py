@@ -232,10 +232,11 @@ def test_ids_out_strided(ops, algo):
 # ---------------------------------------------------------------------------------------------------------------
 # backward
 # ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ["simt", "tcgen05"])
 @pytest.mark.parametrize("mname,training", [("ste", 1), ("rot", 1), ("ste", 0)])
 @pytest.mark.parametrize("shape", [(1024, 32, 256, 3), (777, 64, 512, 4), (64, 16, 32, 2)],
                          ids=lambda s: "n%d_d%d_k%d_L%d" % s)
-def test_backward_vs_oracle_autograd(ops, mname, training, shape):
+def test_backward_vs_oracle_autograd(ops, algo, mname, training, shape):
     n, d, k, L = shape
     beta = 0.4
     x = unit_rows(n, d, seed=21)
@@ -247,21 +248,20 @@ def test_backward_vs_oracle_autograd(ops, mname, training, shape):
     # GPU
     x_d = _dev(x).requires_grad_(True)
     cb_d = _dev(cbs).requires_grad_(True)
-    emb, _r, ids, loss, level_loss = ops.rq_apply(x_d, cb_d, MODES[mname], bool(training), beta, algo="simt")
+    emb, _r, ids, loss, level_loss = ops.rq_apply(x_d, cb_d, MODES[mname], bool(training), beta, algo=algo)
     ((emb.permute(1, 2, 0) * _dev(g_emb)).sum() + (loss * _dev(g_loss)).sum() + (level_loss * _dev(g_ll)).sum()).backward()
     # oracle autograd on the rows whose ids agree (a near-tie row follows another code and so other gradients)
     x_o = x.clone().requires_grad_(True)
     cb_o = [cbs[l].clone().requires_grad_(True) for l in range(L)]
     ref = O.rq_forward(x_o, cb_o, MODES[mname], beta, bool(training))
     rows = (ids.cpu() == ref.sem_ids).all(dim=1)
-    assert rows.float().mean() > 0.995
-    m = rows.float()
-    ((ref.embeddings * g_emb * m[:, None, None]).sum() + (ref.quantize_loss * g_loss * m).sum()
-     + sum((ll * g_ll[l] * m).sum() for l, ll in enumerate(ref.level_losses))).backward()
-    torch.testing.assert_close(x_d.grad.cpu()[rows], x_o.grad[rows], rtol=2e-5, atol=2e-6)
-    if bool(rows.all()):
-        for l in range(L):
-            torch.testing.assert_close(cb_d.grad.cpu()[l], cb_o[l].grad, **GCB)
+    # these seeded inputs hold no near-tie: every id must agree, so the codebook gradients are ALWAYS compared
+    assert bool(rows.all()), f"{int((~rows).sum())} rows follow another code than the oracle; pick seeds without near-ties"
+    ((ref.embeddings * g_emb).sum() + (ref.quantize_loss * g_loss).sum()
+     + sum((ll * g_ll[l]).sum() for l, ll in enumerate(ref.level_losses))).backward()
+    torch.testing.assert_close(x_d.grad.cpu(), x_o.grad, rtol=2e-5, atol=2e-6)
+    for l in range(L):
+        torch.testing.assert_close(cb_d.grad.cpu()[l], cb_o[l].grad, **GCB)
 
 
 def test_backward_broadcast_grad(ops):

@@ -58,6 +58,16 @@ torch.cuda.synchronize()
 t_run = time.perf_counter() - t0
 res = dict(case="kmeans_c3", n=n, d=d, k=k, lloyd_iteration_ms=t_iter, run_s=t_run, run_updates=km.n_iters,
            bytes_per_iteration=n * (4 * d + 8) + k * (d + 1) * 4, hbm_gbs=(n * (4 * d + 8) + k * (d + 1) * 4) / (t_iter * 1e-3) / 1e9)
+# the stress shape of the verdict: K = 4096, D = 64, 65,536 rows (segmented update)
+n4, d4, k4 = 65536, 64, 4096
+x4 = F.normalize(torch.randn(n4, d4, generator=g), dim=-1).cuda()
+cent4 = x4[torch.randperm(n4, generator=g)[:k4].cuda()].clone()
+a4 = ops.kmeans_assign(x4, cent4)
+res["stress_k4096_d64_n65536"] = dict(
+    assign_ms=ev_time(lambda: ops.kmeans_assign(x4, cent4)),
+    assign_tensor_core_ms=ev_time(lambda: ops.kmeans_assign(x4, cent4, exact_diff_form=False)),
+    accumulate_ms=ev_time(lambda: ops.kmeans_accumulate(x4, a4, k4)),
+    finalize_ms=ev_time(lambda: ops.kmeans_finalize(*ops.kmeans_accumulate(x4, a4, k4)[:2], cent4.clone())))
 # CPU oracle: one iteration of the reference algorithm ([N, K, D] difference form)
 torch.set_num_threads(os.cpu_count() or 1)
 cb = cent.cpu().clone()
