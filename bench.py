@@ -293,7 +293,7 @@ def run_native(args):
              hbm_gbs=CHUNK_ITEMS * (4 * DIMS[0] + 4 * EMBED) / (t_enc * 1e-3) / 1e9, traffic=traffic.get("enc_mlp_kernel")),
         dict(kernel="rq_fwd_tc_v11_kernel (fused 3-level quantiser, ids only)", ms=t_rq, bound="tensor", rows_per_launch=CHUNK_ITEMS,
              achieved=FLOP_RQ * CHUNK_ITEMS / (t_rq * 1e-3) / 1e12, peak=pk["tensor_sustained"], unit="TFLOP/s",
-             hbm_gbs=CHUNK_ITEMS * (4 * EMBED + 8 * N_LEVELS) / (t_rq * 1e-3) / 1e9, traffic=traffic.get("rq_fwd_tc_v11_kernel_encode")),
+             hbm_gbs=CHUNK_ITEMS * (4 * EMBED + 8 * N_LEVELS) / (t_rq * 1e-3) / 1e9, traffic=(int(traffic["rq_encode"]["dram_bytes"] * CHUNK_ITEMS / (1 << 22)) if "rq_encode" in traffic else None)),
     ]
     for kk in kernels:
         kk["frac"] = kk["achieved"] / kk["peak"]
@@ -305,7 +305,7 @@ def run_native(args):
                     algorithmic_flop_per_item=FLOP_ENCODER, frac_of_burst_peak=dom["frac_of_burst_peak"],
                     share_of_step=dom["ms"] * n_chunks / step_ms,
                     peak_source=pk["source"] + ", sustained bf16 (the kernel is timed inside a long step; burst = %.1f)" % pk["tensor"],
-                    traffic_source="profiles/r02_traffic.json (ncu --set full, dram read + write per launch of the same shape)",
+                    traffic_source="profiles/r02_traffic.json (ncu --set full, dram read + write of one launch; the quantiser's 4 Mi-row capture is scaled to the rows of this launch)",
                     step=dict(items_per_s=n / (step_ms * 1e-3), tflops=(FLOP_ENCODER + FLOP_RQ) * n / (step_ms * 1e-3) / 1e12,
                               frac_of_sustained_peak=(FLOP_ENCODER + FLOP_RQ) * n / (step_ms * 1e-3) / 1e12 / pk["tensor_sustained"],
                               hbm_gbs=BYTES_ITEM * n / (step_ms * 1e-3) / 1e9),

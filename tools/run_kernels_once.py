@@ -1,5 +1,5 @@
 """A handful of launches of every hot kernel at its bench shape, for `ncu` captures (tools/ncu_capture.sh):
-    python tools/run_kernels_once.py [encoder|rq|train|c4|all]"""
+    python tools/run_kernels_once.py [encoder|rq|train|c4|aux|all]"""
 import os
 import sys
 
@@ -48,5 +48,19 @@ if what in ("c4", "all"):
     packed = ops.pack_codebooks(cbs)
     for _ in range(3):
         ops.rq_encode(x, cbs, packed=packed)
+    torch.cuda.synchronize()
+if what in ("aux", "all"):
+    # stress shapes of the k-means update (segmented form) and the uniqueness loss (sorted form)
+    n, d, k = 65536, 64, 4096
+    x = F.normalize(torch.randn(n, d, device="cuda"), dim=-1)
+    cent = x[torch.randperm(n, device="cuda")[:k]].clone()
+    for _ in range(2):
+        assign = ops.kmeans_assign(x, cent, exact_diff_form=False)
+        sums, counts, _ = ops.kmeans_accumulate(x, assign, k)
+        ops.kmeans_finalize(sums, counts, cent.clone())
+    ids = torch.randint(0, 24, (n, 3), device="cuda")
+    feats = torch.randn(n, 32, device="cuda", requires_grad=True)
+    for _ in range(2):
+        ops.uniqueness_loss(ids, feats, 0.05, 1.0).backward()
     torch.cuda.synchronize()
 print("done", what)
