@@ -123,7 +123,7 @@ int hv_rq_forward(const float* x, int64_t n, int d, const float* codebooks, int 
     return HV_ERR_BAD_SHAPE;
   }
   if (mode == HV_MODE_GUMBEL_SOFTMAX) {
-    set_error("hv_rq_forward: GUMBEL_SOFTMAX has no fused kernel (it needs the dense [N, K] weights); use STE=2 or ROTATION_TRICK=3");
+    set_error("hv_rq_forward: GUMBEL_SOFTMAX takes a temperature and a noise source: call hv_gumbel_forward / hv_gumbel_backward (one level per call); this entry point serves STE=2 and ROTATION_TRICK=3");
     return HV_ERR_UNSUPPORTED;
   }
   if (mode != HV_MODE_STE && mode != HV_MODE_ROTATION_TRICK) {

@@ -360,6 +360,24 @@ __global__ void __launch_bounds__(kThreads) gumbel_bwd_kernel(GumbelArgs a) {
   }
 }
 
+// the draw itself, [N, K]: what the two kernels above generate for (seed, offset) -- for recording / reproducing a step
+__global__ void __launch_bounds__(kThreads) gumbel_uniforms_kernel(GumbelArgs a, float* __restrict__ out) {
+  const int blocks_per_lane = (a.k + 127) / 128;
+  const int64_t total = a.n * 32 * blocks_per_lane;  // one Philox block per thread
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const int jq = static_cast<int>(i % blocks_per_lane);
+    const int lane = static_cast<int>((i / blocks_per_lane) % 32);
+    const int64_t row = i / (static_cast<int64_t>(blocks_per_lane) * 32);
+    float u4[4];
+    draw4(a, row, lane, jq, blocks_per_lane, u4);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int k = lane + 32 * (4 * jq + t);
+      if (k < a.k) out[row * a.k + k] = u4[t];
+    }
+  }
+}
+
 template <int D>
 constexpr int fwd_smem() { return (kMaxK * (D + 4) + kMaxK + kWarps * 32 * (D + 1)) * 4; }
 template <int D>
@@ -413,6 +431,26 @@ int check_common(const char* who, const float* x, int64_t n, int d, const float*
 }  // namespace hv
 
 extern "C" int hv_gumbel_supported(int d, int k) { return (d == 16 || d == 32 || d == 64) && k >= 1 && k <= hv::kMaxK; }
+
+extern "C" int hv_gumbel_uniforms(int64_t n, int k, uint64_t seed, uint64_t offset, float* uniforms, void* stream) {
+  using namespace hv;
+  if (n < 0 || k <= 0) {
+    set_error("hv_gumbel_uniforms: bad shape n=%lld k=%d", static_cast<long long>(n), k);
+    return HV_ERR_BAD_SHAPE;
+  }
+  if (n == 0) return HV_OK;
+  if (!uniforms) {
+    set_error("hv_gumbel_uniforms: null pointer");
+    return HV_ERR_NULL;
+  }
+  GumbelArgs a{};
+  a.n = n, a.k = k, a.seed = seed, a.offset = offset;
+  const int64_t total = n * 32 * ((k + 127) / 128);
+  const int64_t blocks = (total + kThreads - 1) / kThreads;
+  gumbel_uniforms_kernel<<<static_cast<unsigned>(blocks < 65535 ? blocks : 65535), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, uniforms);
+  HV_CUDA_CHECK(cudaGetLastError());
+  return HV_OK;
+}
 
 extern "C" int hv_gumbel_forward(const float* x, int64_t n, int d, const float* codebook, int k, float temperature, float beta,
                                  const float* uniforms, uint64_t seed, uint64_t offset, float* emb_out, int64_t* ids, float* loss,

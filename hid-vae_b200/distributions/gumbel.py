@@ -1,5 +1,6 @@
 """Gumbel-softmax sampling and the temperature schedule (reference distributions/gumbel.py:8-41).
-Only the GUMBEL_SOFTMAX forward mode uses it; that mode stays on PyTorch GPU ops."""
+The GUMBEL_SOFTMAX training forward runs in hv_gumbel_forward (csrc/gumbel.cu) with the same formulas; these functions
+remain for shapes without a fused instantiation and as the API of the reference module."""
 from typing import Tuple
 
 import numpy as np

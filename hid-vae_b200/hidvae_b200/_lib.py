@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p, POINTER
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # .../hid-vae_b200
 LIB_NAME = "libhidvae_b200.so"
@@ -49,6 +49,12 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_size_t, c_void_p]),
     "hv_uniq_backward": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_float, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hv_gumbel_supported": (c_int, [c_int, c_int]),
+    "hv_gumbel_uniforms": (c_int, [c_int64, c_int, c_uint64, c_uint64, c_void_p, c_void_p]),
+    "hv_gumbel_forward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_float, c_void_p, c_uint64, c_uint64,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hv_gumbel_backward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_float, c_float, c_void_p, c_uint64, c_uint64,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hv_encoder_workspace_bytes": (c_size_t, [c_int, POINTER(c_int)]),
     "hv_encoder_pack_weights": (c_int, [POINTER(c_void_p), c_int, POINTER(c_int), c_void_p, c_size_t, c_void_p]),
     "hv_encoder_forward": (c_int, [c_void_p, c_int64, c_int, POINTER(c_int), c_void_p, c_size_t, c_int, c_int, c_void_p,

@@ -204,6 +204,75 @@ def rq_encode(x: Tensor, codebooks: Tensor, algo="auto", ids_out: Optional[Tenso
 # ------------------------------------------------------------------------------------------------------------------
 # fused encoder MLP (modules/encoder.py:23-36) -- inference only: training keeps the PyTorch layers (autograd)
 # ------------------------------------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------------------------
+# Gumbel-softmax level (training mode of QuantizeForwardMode.GUMBEL_SOFTMAX)
+# ---------------------------------------------------------------------------------------------------------------
+def gumbel_supported(d: int, k: int) -> bool:
+    return bool(lib.hv_gumbel_supported(int(d), int(k)))
+
+
+def gumbel_uniforms(n: int, k: int, seed: int, device) -> Tensor:
+    """The [N, K] uniforms the fused Gumbel kernels draw for `seed` (recording / reproducing a step)."""
+    out = torch.empty((n, k), dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        check(lib.hv_gumbel_uniforms(n, k, int(seed), 0, out.data_ptr(), _stream(out)))
+    return out
+
+
+class GumbelFunction(torch.autograd.Function):
+    """Fused Gumbel-softmax level: forward(x [N, D], codebook [K, D], temperature, beta, uniforms [N, K] | None, seed)
+    -> emb_out [N, D], ids [N] (not differentiable), loss [N].  The noise is either the given uniforms (the reference's
+    torch.rand draw) or Philox uniforms of `seed`, regenerated in the backward; dist / logits / weights never reach HBM."""
+
+    @staticmethod
+    def forward(ctx, x, codebook, temperature, beta, uniforms, seed):
+        _require_cuda(x, codebook)
+        x, codebook = _f32c(x), _f32c(codebook)
+        n, d = x.shape
+        k = codebook.shape[0]
+        if uniforms is not None:
+            _require_cuda(uniforms)
+            uniforms = _f32c(uniforms)
+            assert uniforms.shape == (n, k)
+        emb = torch.empty_like(x)
+        ids = torch.empty((n,), dtype=torch.int64, device=x.device)
+        loss = torch.empty((n,), dtype=torch.float32, device=x.device)
+        lse = torch.empty((n,), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.hv_gumbel_forward(x.data_ptr(), n, d, codebook.data_ptr(), k, float(temperature), float(beta), _ptr(uniforms),
+                                        int(seed), 0, emb.data_ptr(), ids.data_ptr(), loss.data_ptr(), lse.data_ptr(), _stream(x)))
+        ctx.save_for_backward(x, codebook, emb, lse, *([uniforms] if uniforms is not None else []))
+        ctx.cfg = (float(temperature), float(beta), int(seed))
+        ctx.mark_non_differentiable(ids)
+        return emb, ids, loss
+
+    @staticmethod
+    def backward(ctx, g_emb, _g_ids, g_loss):
+        x, codebook, emb, lse, *rest = ctx.saved_tensors
+        uniforms = rest[0] if rest else None
+        temperature, beta, seed = ctx.cfg
+        n, d = x.shape
+        k = codebook.shape[0]
+        g_emb = _f32c(g_emb) if g_emb is not None else None
+        g_loss = _f32c(g_loss) if g_loss is not None else None
+        g_x = torch.empty_like(x)
+        g_cb = torch.zeros_like(codebook)
+        with torch.cuda.device(x.device):
+            check(lib.hv_gumbel_backward(x.data_ptr(), n, d, codebook.data_ptr(), k, temperature, beta, _ptr(uniforms), seed, 0,
+                                         emb.data_ptr(), lse.data_ptr(), _ptr(g_emb), _ptr(g_loss), g_x.data_ptr(), g_cb.data_ptr(),
+                                         _stream(x)))
+        return g_x, g_cb, None, None, None, None
+
+
+def gumbel_apply(x: Tensor, codebook: Tensor, temperature: float, beta: float, uniforms: Optional[Tensor] = None,
+                 seed: Optional[int] = None):
+    """(emb_out [N, D], ids [N], loss [N]) of one Gumbel-softmax level.  Without `uniforms` the noise comes from Philox with
+    `seed` (default: a fresh draw from torch's CPU generator, so torch.manual_seed makes a run reproducible)."""
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return GumbelFunction.apply(x, codebook, float(temperature), float(beta), uniforms, int(seed))
+
+
 def _dims_array(dims):
     return (ctypes.c_int * len(dims))(*[int(v) for v in dims])
 

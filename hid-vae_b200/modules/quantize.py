@@ -9,8 +9,11 @@ effective codebook `out_proj(embedding.weight)` (row L2 norm and/or the sim_vq L
 PyTorch: it is K x D, and autograd carries the kernel's codebook gradient back through it.
 
 State-dict keys (`embedding.weight`, `out_proj.0.weight`) equal the reference's, so its checkpoints load.
-GUMBEL_SOFTMAX (dense soft assignment, needs the [N, K] weights) and the COSINE distance (selected by nothing in
-HiD-VAE) run on PyTorch GPU ops with the reference's formulas.  CPU tensors are rejected: there is no CPU path.
+GUMBEL_SOFTMAX (the class default; training mode :125-130) is one fused kernel per level and direction as well
+(`hv_gumbel_forward/backward`: distance, in-kernel Philox noise, softmax and the soft gather `w @ codebook` without any
+[N, K] tensor in memory); its eval mode is the same fused kernel as STE.  Only the COSINE distance (selected by nothing
+in HiD-VAE) and Gumbel shapes outside D in {16, 32, 64}, K <= 256 run on PyTorch GPU ops with the reference's formulas.
+CPU tensors are rejected: there is no CPU path.
 """
 from enum import Enum
 from typing import NamedTuple, Optional
@@ -137,10 +140,16 @@ class Quantize(nn.Module):
             if self.training and self.forward_mode == QuantizeForwardMode.ROTATION_TRICK and x.shape[0] == 1:
                 emb_out = emb_out.squeeze()  # the reference's transform ends in .squeeze() (quantize.py:45)
             return QuantizeOutput(embeddings=emb_out, ids=ids[:, 0], loss=loss)
+        if (self.forward_mode == QuantizeForwardMode.GUMBEL_SOFTMAX and self.distance_mode == QuantizeDistance.L2
+                and ops.gumbel_supported(self.embed_dim, self.n_embed)):
+            # training, soft assignment (reference :125-130): one fused kernel, noise from Philox (seeded by torch's generator)
+            emb_out, ids, loss = ops.gumbel_apply(x, codebook, float(temperature), self.commitment_weight)
+            return QuantizeOutput(embeddings=emb_out, ids=ids, loss=loss)
         return self._forward_dense(x, codebook, temperature)
 
     def _forward_dense(self, x: Tensor, codebook: Tensor, temperature: float) -> QuantizeOutput:
-        """GUMBEL_SOFTMAX and/or COSINE: dense [N, K] path on PyTorch GPU ops (reference :108-148)."""
+        """COSINE distance, or a Gumbel shape without a fused instantiation: dense [N, K] path on PyTorch GPU ops
+        (reference :108-148)."""
         if self.distance_mode == QuantizeDistance.L2:
             dist = (x ** 2).sum(dim=1, keepdim=True) + (codebook.T ** 2).sum(dim=0, keepdim=True) - 2 * x @ codebook.T
         else:

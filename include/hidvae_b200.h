@@ -76,7 +76,7 @@ size_t hv_workspace_bytes(int op, int64_t n, int d, int k, int n_levels);
  *
  *   x           [N, D]     level-0 input (the encoder output)
  *   codebooks   [L, K, D]  effective codebooks
- *   mode        HV_MODE_STE | HV_MODE_ROTATION_TRICK (GUMBEL_SOFTMAX: HV_ERR_UNSUPPORTED, kept in PyTorch)
+ *   mode        HV_MODE_STE | HV_MODE_ROTATION_TRICK (GUMBEL_SOFTMAX: HV_ERR_UNSUPPORTED here -- hv_gumbel_forward)
  *   training    1: emb_out = e (STE value) or the rotated vector; 0: eval semantics emb_out = e
  *   beta        commitment weight; loss_l = (1 + beta) * |r_l - e_l|^2 computed as a + beta*a
  *   ids         int64, element (row, level) at ids[row*ids_row_stride + level*ids_level_stride]
@@ -160,6 +160,33 @@ int hv_uniq_forward(const int64_t* ids, int64_t rows, int64_t width, int64_t row
 int hv_uniq_backward(const int64_t* ids, int64_t rows, int64_t width, int64_t row_stride, int64_t col_stride,
                      const float* feats, int d, float margin, float weight, const double* stats,
                      const float* g_out, float* g_feats, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Gumbel-softmax quantiser level, training mode (modules/quantize.py:108-130,144; distributions/gumbel.py:8-18) -- the
+ * [N, K] tables of the reference (dist, noise, logits, weights and their autograd copies) never exist in memory:
+ *   dist_k = |x|^2 + |c_k|^2 - 2 x.c_k;  ids = argmin_k dist_k;  g_k = -log(-log(u_k + 1e-20) + 1e-20);
+ *   w = softmax((-dist + g) / temperature);  emb_out = w @ codebook;  loss = (1 + beta) |x - emb_out|^2 per row.
+ * Noise: `uniforms` [N, K] (the reference's torch.rand draw; parity tests) or, when NULL, counter-based Philox4x32-10
+ *   uniforms from (seed, offset) -- the backward regenerates the same draw from the same pair (one call consumes
+ *   32 * ceil(K / 128) counters per row starting at `offset`).
+ * Forward writes emb_out [N, D], lse [N] (log-sum-exp of the logits, consumed by the backward) and, when non-NULL,
+ *   ids [N] int64 and loss [N].
+ * Backward: g_emb [N, D] (may be NULL = 0), g_loss [N] (may be NULL = 0) -> g_x [N, D] (overwritten) and g_codebook [K, D]
+ *   (ACCUMULATED into: the caller zeroes it).  Gradients are those of the reference's autograd graph: through the softmax
+ *   weights and the distance table to x and the codebook, through w @ codebook to the codebook, and the two halves of
+ *   QuantizeLoss (modules/loss.py:41-44).
+ * Served shapes: D in {16, 32, 64}, K <= 256 (hv_gumbel_supported); others return HV_ERR_UNSUPPORTED.
+ * hv_gumbel_uniforms writes the [N, K] uniforms the two kernels generate for (seed, offset): recording a step's draw, and
+ *   the test that the Philox path equals the explicit-noise path.
+ */
+int hv_gumbel_supported(int d, int k);
+int hv_gumbel_uniforms(int64_t n, int k, uint64_t seed, uint64_t offset, float* uniforms, void* stream);
+int hv_gumbel_forward(const float* x, int64_t n, int d, const float* codebook, int k, float temperature, float beta,
+                      const float* uniforms, uint64_t seed, uint64_t offset, float* emb_out, int64_t* ids, float* loss,
+                      float* lse, void* stream);
+int hv_gumbel_backward(const float* x, int64_t n, int d, const float* codebook, int k, float temperature, float beta,
+                       const float* uniforms, uint64_t seed, uint64_t offset, const float* emb_out, const float* lse,
+                       const float* g_emb, const float* g_loss, float* g_x, float* g_codebook, void* stream);
 
 /*
  * Fused encoder MLP in front of the quantiser: z = [l2norm](W_L silu(... silu(W_1 x))) -- the bias-free Linear + SiLU

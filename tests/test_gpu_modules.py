@@ -57,7 +57,8 @@ def test_quantize_module_matches_reference(mods, golden_dir, mname, normalize, t
 
 
 def test_quantize_gumbel_and_errors(mods, golden_dir):
-    """GUMBEL_SOFTMAX stays on PyTorch GPU ops: same ids, value within the noise-free part; CPU input is refused."""
+    """GUMBEL_SOFTMAX through the module (fused hv_gumbel_forward in training, the STE kernel in eval): ids equal the
+    reference recording in both modes; CPU input is refused.  Values / gradients: tests/test_gpu_gumbel.py."""
     g = npz(golden_dir, "quantize_levels.npz")
     layer = mods.Quantize(32, 64, do_kmeans_init=False, commitment_weight=0.25,
                           forward_mode=mods.QuantizeForwardMode.GUMBEL_SOFTMAX).cuda()

@@ -94,3 +94,25 @@ for b in (128, 1024, 8192, 65536):
     t_cnt = ev_time(lambda: ops.count_rows_with_later_twin(ids), reps=5)
     print(json.dumps(dict(case="uniqueness", batch=b, fwd_bwd_ms=t, p_unique_ms=t_cnt, pairs=b * (b - 1) // 2,
                           pair_rate_g_per_s=b * (b - 1) / 2 / (t * 1e-3) / 1e9)))
+
+# ---- Gumbel-softmax level (modules/quantize.py:125-130): fused kernels vs the dense PyTorch formulas on the same GPU ----
+from distributions.gumbel import gumbel_softmax_sample
+for nb in (1024, 8192, 65536):
+    gi = torch.Generator().manual_seed(nb)
+    xg = F.normalize(torch.randn(nb, 32, generator=gi), dim=-1).cuda().requires_grad_(True)
+    cbg = F.normalize(torch.rand(256, 32, generator=gi), dim=-1).cuda().requires_grad_(True)
+
+    def fused():
+        emb, _ids, loss = ops.gumbel_apply(xg, cbg, 0.2, 0.25, seed=7)
+        xg.grad = cbg.grad = None
+        (emb.sum() + loss.sum()).backward()
+
+    def dense():
+        dist = (xg ** 2).sum(dim=1, keepdim=True) + (cbg.T ** 2).sum(dim=0, keepdim=True) - 2 * xg @ cbg.T
+        emb = gumbel_softmax_sample(-dist, 0.2, xg.device) @ cbg
+        loss = ((xg.detach() - emb) ** 2).sum(-1) + 0.25 * ((xg - emb.detach()) ** 2).sum(-1)
+        xg.grad = cbg.grad = None
+        (emb.sum() + loss.sum()).backward()
+
+    print(json.dumps(dict(case="gumbel_level_fwd_bwd", rows=nb, d=32, k=256, fused_ms=ev_time(fused, reps=5),
+                          dense_torch_ms=ev_time(dense, reps=5))))
