@@ -75,13 +75,32 @@ bool rq_fwd_tc_supported(int d, int k, int n_levels);
 size_t rq_fwd_tc_workspace_bytes(int d, int k, int n_levels);
 size_t rq_bwd_workspace_bytes(int64_t n, int d, int k, int n_levels);
 
+// 1 / (sqrt(v) + eps) and 1 / max(sqrt(v), floor) on the special-function unit: sqrt.approx (max relative error 2^-23) and
+// rcp.approx followed by one Newton step (the reciprocal is then correctly rounded up to the last bit of its argument).
+// 6 instructions instead of the ~16 + slow-path branches of an IEEE sqrt and division; three of these per row and level.
+__device__ __forceinline__ float fast_rcp(float d) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return fmaf(fmaf(-d, r, 1.0f), r, r);
+}
+__device__ __forceinline__ float fast_inv_norm_eps(float v, float eps) {
+  float s;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(v));
+  return fast_rcp(s + eps);
+}
+__device__ __forceinline__ float fast_inv_norm_floor(float v, float floor) {
+  float s;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(v));
+  return fast_rcp(fmaxf(s, floor));
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Per-row "tail" of one quantiser level: everything after the argmin.  One thread owns one row in registers.
 //   r      in : residual entering the level (r_l)            out: r_{l+1} = r_l - o_l
 //   e         : the chosen code row C_l[id] (fp32)
 //   returns the level loss a + beta*a with a = |r - e|^2      (modules/loss.py:41-44)
 //   o (emb_out) is written to `o_out` when non-null.
-// ROT implements modules/quantize.py:34-45,134-140 literally:  o = r - 2 (r.w) w + 2 (r.u) q
+// ROT implements modules/quantize.py:34-45,134-140:  o = r - 2 (r.w) w + 2 (r.u) q  (collapsed to two row passes, below)
 // ---------------------------------------------------------------------------------------------------------
 template <int D, bool ROT>
 __device__ __forceinline__ float rq_level_tail_o(float (&r)[D], const float (&e)[D], float beta, float (&o)[D]) {
@@ -96,34 +115,27 @@ __device__ __forceinline__ float rq_level_tail_o(float (&r)[D], const float (&e)
 #pragma unroll
     for (int i = 0; i < D; ++i) o[i] = e[i];
   } else {
+    // o = r - 2 (r.w) w + 2 (r.u) q with u = r ir, q = e ie, w = (u + q) is collapses to  o = cr r + ce e  with scalars
+    // that follow from the three row sums r.r, e.e, r.e (r.e from the loss sum: |r - e|^2 = r.r + e.e - 2 r.e):
+    //   r.u = rr ir,  r.q = re ie,  |u + q|^2 = rr ir^2 + ee ie^2 + 2 re ir ie,
+    //   a2 = 2 (r.u + r.q) is^2,  cr = 1 - a2 ir,  ce = (2 r.u - a2) ie.
+    // Two passes over the row instead of five (the backward recomputes the chain with the same expressions).
     float rr = 0.f, ee = 0.f;
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       rr = fmaf(r[i], r[i], rr);
       ee = fmaf(e[i], e[i], ee);
     }
-    const float inv_r = 1.0f / (sqrtf(rr) + 1e-8f);  // u = r / (|r| + 1e-8)
-    const float inv_e = 1.0f / (sqrtf(ee) + 1e-8f);  // q = e / (|e| + 1e-8)
-    float ss = 0.f, ru = 0.f, rs = 0.f;
+    const float re = 0.5f * ((rr + ee) - a);
+    const float inv_r = fast_inv_norm_eps(rr, 1e-8f);  // u = r / (|r| + 1e-8)
+    const float inv_e = fast_inv_norm_eps(ee, 1e-8f);  // q = e / (|e| + 1e-8)
+    const float ru = rr * inv_r, rq = re * inv_e;
+    const float ss = fmaf(2.0f * rq, inv_r, fmaf(ru, inv_r, ee * inv_e * inv_e));
+    const float inv_s = fast_inv_norm_floor(ss, 1e-6f);  // w = (u + q) / max(|u + q|, 1e-6)
+    const float a2 = 2.0f * (ru + rq) * inv_s * inv_s;
+    const float cr = 1.0f - a2 * inv_r, ce = (2.0f * ru - a2) * inv_e;
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-      const float u = r[i] * inv_r;
-      const float q = e[i] * inv_e;
-      const float s = u + q;
-      ss = fmaf(s, s, ss);
-      ru = fmaf(r[i], u, ru);
-      rs = fmaf(r[i], s, rs);
-    }
-    const float inv_s = 1.0f / fmaxf(sqrtf(ss), 1e-6f);  // w = (u+q) / max(|u+q|, 1e-6)
-    const float rw2 = 2.0f * (rs * inv_s);               // 2 (r.w)
-    const float ru2 = 2.0f * ru;                         // 2 (r.u)
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      const float u = r[i] * inv_r;
-      const float q = e[i] * inv_e;
-      const float w = (u + q) * inv_s;
-      o[i] = r[i] - rw2 * w + ru2 * q;
-    }
+    for (int i = 0; i < D; ++i) o[i] = fmaf(cr, r[i], ce * e[i]);
   }
 #pragma unroll
   for (int i = 0; i < D; ++i) r[i] = r[i] - o[i];

@@ -335,14 +335,26 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mlp_kernel(EncArgs a) {
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(h_ready));
     };
 
+    // instrumented builds (-DHV_TC_INSTRUMENT): mean cycles per tile of every phase as seen by epilogue warp 0 of CTA 0,
+    // accumulated in registers and printed once after the last tile (a printf inside the loop perturbs the pipeline)
+#ifdef HV_TC_INSTRUMENT
+    long long ts[12], ts_sum[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define ENC_STAMP(j) ts[j] = clock64()
+#else
+#define ENC_STAMP(j)
+#endif
     int pre = 0;  // chunks of the current tile converted ahead of time
     for (int i = 0; i < my_tiles; ++i) {
+      ENC_STAMP(0);
       convert(i, pre, kChunks);
+      ENC_STAMP(1);
       // ---- layer 1 -> h1 (in place: half 0 packs [0,256) upwards into [0,128), half 1 packs [256,512) downwards into [384,512)) ----
       wait_d();
+      ENC_STAMP(2);
       if (hf == 0) epilogue_pack<8, false, PRECISE>(tl, tl);
       else epilogue_pack<8, true, PRECISE>(tl + 256, tl + kColH1b);
       signal_h();
+      ENC_STAMP(3);
       // the next tile's first chunks while layer 2 runs (their stages were freed by layer 1's commits)
       pre = 0;
       if (i + 1 < my_tiles) {
@@ -350,15 +362,21 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mlp_kernel(EncArgs a) {
         pre = kAStages;
       }
       // ---- layer 2 -> h2 [0,128) ----
+      ENC_STAMP(4);
       wait_d();
+      ENC_STAMP(5);
       epilogue_pack<4, false, PRECISE>(tl + kColD2 + 128 * hf, tl + 64 * hf);
       signal_h();
+      ENC_STAMP(6);
       // ---- layer 3 -> h3 [128,192) ----
       wait_d();
+      ENC_STAMP(7);
       epilogue_pack<2, false, PRECISE>(tl + kColD3 + 64 * hf, tl + kColH3 + 32 * hf);
       signal_h();
+      ENC_STAMP(8);
       // ---- layer 4 -> z ----
       wait_d();
+      ENC_STAMP(9);
       if (hf == 0) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(tl + kColD4, v);
@@ -395,7 +413,20 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mlp_kernel(EncArgs a) {
       } else {
         signal_h();
       }
+#ifdef HV_TC_INSTRUMENT
+      ENC_STAMP(10);
+      if (i > 0)
+        for (int j = 0; j < 10; ++j) ts_sum[j] += ts[j + 1] - ts[j];
+#endif
     }
+#ifdef HV_TC_INSTRUMENT
+    if (blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32 && my_tiles > 1) {
+      const long long t = my_tiles - 1;
+      printf("ENC mean cycles per tile over %lld tiles: convert %lld | wait L1 %lld | epi1 %lld | preconvert %lld | wait L2 %lld | epi2 %lld | wait L3 %lld | epi3 %lld | wait L4 %lld | out %lld\n",
+             t, ts_sum[0] / t, ts_sum[1] / t, ts_sum[2] / t, ts_sum[3] / t, ts_sum[4] / t, ts_sum[5] / t, ts_sum[6] / t, ts_sum[7] / t,
+             ts_sum[8] / t, ts_sum[9] / t);
+    }
+#endif
   }
 
   ptx::tc_fence_before_sync();

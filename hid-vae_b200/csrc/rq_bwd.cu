@@ -102,20 +102,20 @@ __global__ void __launch_bounds__(kBwdThreads, NL > 0 ? HV_BWD_MINB : 1) rq_bwd_
         E[l] = e;
         float4 o = e;
         if (rot) {
-          // modules/quantize.py:34-45 with u = r ir, q = e ie, s = u + q.  r.u = rr ir and r.s = rr ir + re ie follow from
-          // the row sums r.r, e.e, r.e (4 shuffle reductions instead of 5); |s|^2 stays the literal sum: 1/|s| scales the
-          // Jacobian term, and its rounding must stay at the reference's level (a product form cost 3e-7 of |g| there)
+          // modules/quantize.py:34-45 with u = r ir, q = e ie, s = u + q.  r.u = rr ir, r.s = rr ir + re ie and |s|^2 all
+          // follow from the three row sums r.r, e.e, r.e (3 shuffle reductions instead of 5)
           const float rr = group_sum<LPR>(dot4(r, r));
           const float ee = group_sum<LPR>(dot4(e, e));
           const float re = group_sum<LPR>(dot4(r, e));
-          const float ir = 1.0f / (sqrtf(rr) + 1e-8f);
-          const float ie = 1.0f / (sqrtf(ee) + 1e-8f);
+          const float ir = fast_inv_norm_eps(rr, 1e-8f);
+          const float ie = fast_inv_norm_eps(ee, 1e-8f);
           const float ru = rr * ir;
           const float rq = re * ie;
-          const float4 sv = make_float4(fmaf(r.x, ir, e.x * ie), fmaf(r.y, ir, e.y * ie), fmaf(r.z, ir, e.z * ie), fmaf(r.w, ir, e.w * ie));
-          const float ss = group_sum<LPR>(dot4(sv, sv));
+          // |u + q|^2 = |u|^2 + |q|^2 + 2 u.q from the three row sums already at hand (one shuffle reduction and a vector
+          // pass less per level; absolute error ~4e-7 on a value in [0, 4], i.e. 1e-7 relative on 1/|s| away from r = -e)
+          const float ss = fmaf(2.0f * rq, ir, fmaf(ru, ir, ee * ie * ie));
           const float rs = ru + rq;
-          const float is = 1.0f / fmaxf(sqrtf(ss), 1e-6f);
+          const float is = fast_inv_norm_floor(ss, 1e-6f);
           inv_r[l] = ir, inv_e[l] = ie, inv_s[l] = is;
           // o = r - 2 (r.w) w + 2 (r.u) q  with w = (u + q) is:   o = r (1 - a ir) + e (b - a) ie,  a = 2 rs is^2, b = 2 ru
           const float a2 = 2.0f * rs * is * is, b2 = 2.0f * ru;
@@ -186,6 +186,148 @@ __global__ void __launch_bounds__(kBwdThreads, NL > 0 ? HV_BWD_MINB : 1) rq_bwd_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Large-N variant for codebooks that fit in shared memory (L K D 4 <= 96 KB: every HiD-VAE config).  Same arithmetic, two
+// changes that remove the memory latency the kernel above exposes per row (ncu: stall_long_scoreboard 39 % of warp time):
+//   * the fp32 codebooks are staged in shared memory once per persistent CTA (2 CTAs per SM): the id -> code row gather
+//     is an LDS.128 instead of a dependent round trip to L2 (and 4 L D bytes per row less L2 traffic);
+//   * the row's inputs (x, ids, g_emb, g_loss) are loaded ONE ITERATION AHEAD into registers, so no load of the current
+//     row is ever waited for.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef HV_BWD2_THREADS
+#define HV_BWD2_THREADS 320
+#endif
+constexpr int kBwd2Threads = HV_BWD2_THREADS;
+constexpr int kBwd2SmemLimit = 96 * 1024;
+
+template <int D, bool ROT, bool TRAIN, int NL>
+__global__ void __launch_bounds__(kBwd2Threads, 2) rq_bwd_smem_kernel(RqBwdArgs a) {
+  constexpr int LPR = D / 4;
+  constexpr int ROWS_PER_WARP = 32 / LPR;
+  constexpr bool rot = ROT && TRAIN;
+  extern __shared__ __align__(16) float s_cb[];  // [NL][K][D]
+  {
+    const int total4 = NL * a.k * (D / 4);
+    for (int i = threadIdx.x; i < total4; i += kBwd2Threads)
+      reinterpret_cast<float4*>(s_cb)[i] = __ldg(reinterpret_cast<const float4*>(a.codebooks) + i);
+  }
+  __syncthreads();
+
+  const int64_t lkd = static_cast<int64_t>(NL) * a.k * D;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int warp_global = (blockIdx.x * kBwd2Threads + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * kBwd2Threads) >> 5;
+  const int64_t n_groups = (a.n + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
+  float* gc_base = a.n_replicas > 0 ? a.replicas + static_cast<int64_t>(blockIdx.x % a.n_replicas) * lkd : a.g_codebooks;
+
+  // the next iteration's inputs
+  float4 nx, nge[NL];
+  int nid[NL];
+  float ngl;
+  auto fetch = [&](int64_t g) {
+    const int64_t row = g * ROWS_PER_WARP + lane / LPR;
+    const int64_t rrow = row < a.n ? row : 0;  // keep every lane in the shuffles; the stores are masked
+    nx = __ldg(reinterpret_cast<const float4*>(a.x + rrow * D) + sub);
+    ngl = a.g_loss != nullptr ? __ldg(a.g_loss + rrow * a.g_loss_stride) : 0.f;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      int64_t code = __ldg(a.ids + rrow * a.ids_row_stride + l * a.ids_level_stride);
+      code = code < 0 ? 0 : (code >= a.k ? a.k - 1 : code);
+      nid[l] = static_cast<int>(code);
+      nge[l] = a.g_emb != nullptr ? __ldg(reinterpret_cast<const float4*>(a.g_emb + l * a.g_emb_level_stride + rrow * a.g_emb_row_stride) + sub)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if (warp_global < n_groups) fetch(warp_global);
+
+  for (int64_t g = warp_global; g < n_groups; g += n_warps) {
+    const int64_t row = g * ROWS_PER_WARP + lane / LPR;
+    const bool valid = row < a.n;
+    float4 r = nx;
+    const float gl = ngl;
+    float4 GE[NL];
+    int id[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) GE[l] = nge[l], id[l] = nid[l];
+    if (g + n_warps < n_groups) fetch(g + n_warps);
+
+    float4 R[NL], E[NL];
+    float inv_r[NL], inv_e[NL], inv_s[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const float4 e = *reinterpret_cast<const float4*>(s_cb + (static_cast<int64_t>(l) * a.k + id[l]) * D + sub * 4);
+      R[l] = r;
+      E[l] = e;
+      float4 o = e;
+      if (rot) {  // (same expressions as rq_bwd_kernel)
+        const float rr = group_sum<LPR>(dot4(r, r));
+        const float ee = group_sum<LPR>(dot4(e, e));
+        const float re = group_sum<LPR>(dot4(r, e));
+        const float ir = fast_inv_norm_eps(rr, 1e-8f);
+        const float ie = fast_inv_norm_eps(ee, 1e-8f);
+        const float ru = rr * ir;
+        const float rq = re * ie;
+        // |u + q|^2 = |u|^2 + |q|^2 + 2 u.q from the three row sums already at hand (one shuffle reduction and a vector
+        // pass less per level; absolute error ~4e-7 on a value in [0, 4], i.e. 1e-7 relative on 1/|s| away from r = -e)
+        const float ss = fmaf(2.0f * rq, ir, fmaf(ru, ir, ee * ie * ie));
+        const float rs = ru + rq;
+        const float is = fast_inv_norm_floor(ss, 1e-6f);
+        inv_r[l] = ir, inv_e[l] = ie, inv_s[l] = is;
+        const float a2 = 2.0f * rs * is * is, b2 = 2.0f * ru;
+        const float cr = 1.0f - a2 * ir, ce = (b2 - a2) * ie;
+        o.x = fmaf(cr, r.x, ce * e.x);
+        o.y = fmaf(cr, r.y, ce * e.y);
+        o.z = fmaf(cr, r.z, ce * e.z);
+        o.w = fmaf(cr, r.w, ce * e.w);
+      }
+      r = make_float4(r.x - o.x, r.y - o.y, r.z - o.z, r.w - o.w);
+    }
+
+    float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = NL - 1; l >= 0; --l) {
+      const float4 ge = GE[l];
+      float4 h = make_float4(ge.x - G.x, ge.y - G.y, ge.z - G.z, ge.w - G.w);
+      const float4 rl = R[l], el = E[l];
+      const float4 diff = make_float4(rl.x - el.x, rl.y - el.y, rl.z - el.z, rl.w - el.w);
+      const float c2 = 2.0f * gl;
+      float4 ge_code = make_float4(-c2 * diff.x, -c2 * diff.y, -c2 * diff.z, -c2 * diff.w);
+      const float cb2 = a.beta * c2;
+      if (TRAIN) {
+        float4 jh = h;
+        if (rot) {
+          const float ir = inv_r[l], ie = inv_e[l], is = inv_s[l];
+          const float4 u = make_float4(rl.x * ir, rl.y * ir, rl.z * ir, rl.w * ir);
+          const float4 q = make_float4(el.x * ie, el.y * ie, el.z * ie, el.w * ie);
+          const float4 w = make_float4((u.x + q.x) * is, (u.y + q.y) * is, (u.z + q.z) * is, (u.w + q.w) * is);
+          const float hw2 = 2.0f * group_sum<LPR>(dot4(h, w));
+          const float hq2 = 2.0f * group_sum<LPR>(dot4(h, q));
+          jh.x = h.x - hw2 * w.x + hq2 * u.x;
+          jh.y = h.y - hw2 * w.y + hq2 * u.y;
+          jh.z = h.z - hw2 * w.z + hq2 * u.z;
+          jh.w = h.w - hw2 * w.w + hq2 * u.w;
+        }
+        G.x += jh.x + cb2 * diff.x, G.y += jh.y + cb2 * diff.y;
+        G.z += jh.z + cb2 * diff.z, G.w += jh.w + cb2 * diff.w;
+      } else {
+        G.x += cb2 * diff.x, G.y += cb2 * diff.y, G.z += cb2 * diff.z, G.w += cb2 * diff.w;
+        ge_code.x += h.x, ge_code.y += h.y, ge_code.z += h.z, ge_code.w += h.w;
+      }
+      if (valid) red_add_v4(gc_base + (static_cast<int64_t>(l) * a.k + id[l]) * D + sub * 4, ge_code);
+    }
+    if (valid) reinterpret_cast<float4*>(a.g_x + row * D)[sub] = G;
+  }
+}
+
+// shapes the shared-memory variant serves: exact-level instantiation, codebooks within 96 KB, no per-level loss gradient,
+// and enough rows for 2 persistent CTAs per SM to amortise staging the codebooks
+template <int D>
+bool bwd_smem_ok(const RqBwdArgs& a) {
+  return (D == 16 || D == 32 || D == 64) && a.n_levels >= 1 && a.n_levels <= 4 && a.g_level_loss == nullptr && a.n >= 65536 &&
+         static_cast<int64_t>(a.n_levels) * a.k * D * 4 <= kBwd2SmemLimit;
+}
+
 template <int D>
 int launch_d(const RqBwdArgs& a, bool rot, cudaStream_t stream) {
   DeviceProps props;
@@ -202,8 +344,22 @@ int launch_d(const RqBwdArgs& a, bool rot, cudaStream_t stream) {
   };
   const bool train = a.training != 0;
   const bool r = rot && train;  // eval: the rotation plays no part
+  const bool smem_variant = bwd_smem_ok<D>(a);
+  const int smem_bytes = a.n_levels * a.k * D * 4;
+  auto go2 = [&](auto kernel) -> int {
+    if (int st = prepare_kernel(kernel, 0, smem_bytes)) return st;
+    kernel<<<2 * props.sm_count, kBwd2Threads, smem_bytes, stream>>>(a);
+    HV_CUDA_CHECK(cudaGetLastError());
+    return HV_OK;
+  };
   auto pick = [&](auto nl) -> int {
     constexpr int NLc = decltype(nl)::value;
+    if constexpr (NLc > 0 && (D == 16 || D == 32 || D == 64)) {
+      if (smem_variant) {
+        if (r) return go2(rq_bwd_smem_kernel<D, true, true, NLc>);
+        return train ? go2(rq_bwd_smem_kernel<D, false, true, NLc>) : go2(rq_bwd_smem_kernel<D, false, false, NLc>);
+      }
+    }
     if (r) return go(rq_bwd_kernel<D, true, true, NLc>);
     return train ? go(rq_bwd_kernel<D, false, true, NLc>) : go(rq_bwd_kernel<D, false, false, NLc>);
   };
