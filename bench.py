@@ -419,43 +419,51 @@ def run_train_dp(rank, world, dev):
             res["allreduce_checked"] = False
             res["allreduce_check"] = f"peer-memory exchange unavailable: {type(e).__name__}: {e}"
 
-    for bs in (128, 8192):
-        def step():
-            idx = torch.randint(0, n_items, (bs,), device=dev, generator=g)
-            batch = TaggedSeqBatch(None, None, None, x[idx], None, None, tags_emb[idx], tags_idx[idx])
-            grads.zero()
-            out = model(batch, gumbel_t=0.2)
-            out.loss.backward()
-            grads.all_reduce()
-            opt.step()
-            return out.loss
+    from hidvae_b200.graph_step import GraphedTrainStep
+    fetch = lambda idx: TaggedSeqBatch(None, None, None, x[idx], None, None, tags_emb[idx], tags_idx[idx])
+    opt_g = torch.optim.AdamW(model.parameters(), lr=torch.tensor(1e-4, device=dev), weight_decay=0.01, capturable=True)
 
-        for _ in range(5):
-            step()
+    def timed(fn, reps):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        reps = 30
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(reps):
-            loss = step()
+            fn()
         b.record()
         torch.cuda.synchronize()
         ms = torch.tensor([a.elapsed_time(b) / reps], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for bs in (128, 8192):
+        last = {}
+
+        def step():   # the eager step: what a line-by-line port of train_hidvae.py:700-770 costs (launch-bound)
+            grads.zero()
+            out = model(fetch(torch.randint(0, n_items, (bs,), device=dev, generator=g)), gumbel_t=0.2)
+            out.loss.backward()
+            grads.all_reduce()
+            opt.step()
+            last["loss"] = out.loss
+
+        for _ in range(5):
+            step()
+        eager_ms = timed(step, 20)
+        # the same step as two CUDA-graph replays around the NCCL exchange (hidvae_b200/graph_step.py)
+        graphed = GraphedTrainStep(model, opt_g, grads, fetch, bs, n_items, gumbel_t=0.2, generator=g, warmup=3)
+        for _ in range(3):
+            graphed()
+        ms = timed(graphed, 50)
         # the exchange alone (NCCL, 29 MB) on the same buffer
-        ar_ms = None
-        if world > 1:
-            a.record()
-            for _ in range(20):
-                dist.all_reduce(grads.flat)
-            b.record()
-            torch.cuda.synchronize()
-            ar_ms = a.elapsed_time(b) / 20
-        res[f"batch{bs}_per_rank"] = dict(ms_per_step=float(ms.item()), items_per_s=world * bs / (float(ms.item()) * 1e-3),
-                                           flat_allreduce_ms=ar_ms, loss=float(loss.detach()))
+        ar_ms = timed(lambda: dist.all_reduce(grads.flat), 20) if world > 1 else None
+        res[f"batch{bs}_per_rank"] = dict(ms_per_step=ms, items_per_s=world * bs / (ms * 1e-3), eager_ms_per_step=eager_ms,
+                                           eager_items_per_s=world * bs / (eager_ms * 1e-3), flat_allreduce_ms=ar_ms,
+                                           loss=float(graphed.stats[0]), step="CUDA graphs: gather + forward + backward | NCCL "
+                                           "all-reduce of the flat gradient | AdamW")
+        del graphed
     return res
 
 

@@ -269,6 +269,9 @@ def gumbel_apply(x: Tensor, codebook: Tensor, temperature: float, beta: float, u
     """(emb_out [N, D], ids [N], loss [N]) of one Gumbel-softmax level.  Without `uniforms` the noise comes from Philox with
     `seed` (default: a fresh draw from torch's CPU generator, so torch.manual_seed makes a run reproducible)."""
     if seed is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("gumbel_apply under CUDA-graph capture: the noise seed is a host scalar and would be frozen into "
+                               "the graph (every replay the same draw); run Gumbel-softmax steps eagerly")
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     return GumbelFunction.apply(x, codebook, float(temperature), float(beta), uniforms, int(seed))
 

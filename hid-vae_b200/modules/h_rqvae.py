@@ -302,7 +302,7 @@ class HRqVae(nn.Module, _HubMixin):
         dev = encoded_x.device
         emb, residuals, sem_ids, quantize_loss = self.quantize_all_levels(encoded_x, gumbel_t, want_residuals=_want_residuals)
 
-        zero = lambda: torch.tensor(0.0, device=dev)
+        zero = lambda: torch.zeros((), device=dev)
         align_total, pred_total, acc_total = zero(), zero(), zero()
         align_by_layer, pred_by_layer, acc_by_layer = [], [], []
         have_tags = tags_emb is not None and tags_indices is not None

@@ -90,17 +90,18 @@ class TagPredictionLoss(nn.Module):
     # -- helpers ---------------------------------------------------------------------------------------------
     def _soft_targets(self, logits: Tensor, targets: Tensor, gamma: float) -> Tensor:
         n_cls = logits.shape[-1]
-        hot = F.one_hot(targets, n_cls).to(logits.dtype)
+        hot = torch.zeros_like(logits).scatter_(1, targets.unsqueeze(1), 1.0)   # (no host-side range check: capturable)
         if self.use_label_smoothing and logits.requires_grad:
             eps = min(0.25, self.label_smoothing_alpha + 0.015 * gamma + min(0.3, 0.05 * (n_cls / 100)))
             hot = hot * (1.0 - eps) + eps / n_cls
         return hot
 
+    # the three loss forms return ONE VALUE PER ROW; `forward` averages them over the rows with a valid target
     def _focal_loss_with_smoothing(self, logits: Tensor, targets: Tensor, gamma: float = 2.0, alpha: float = 0.25) -> Tensor:
         soft = self._soft_targets(logits, targets, gamma)
         logp = F.log_softmax(logits, dim=-1)
         pt = (soft * logp.exp()).sum(dim=1)
-        return (alpha * (1.0 - pt).pow(gamma) * -(soft * logp).sum(dim=1)).mean()
+        return alpha * (1.0 - pt).pow(gamma) * -(soft * logp).sum(dim=1)
 
     def _focal_loss_with_weights_and_smoothing(self, logits: Tensor, targets: Tensor, gamma: float = 2.0,
                                                class_weights: Optional[Tensor] = None) -> Tensor:
@@ -111,10 +112,10 @@ class TagPredictionLoss(nn.Module):
         pt = (soft * probs).sum(dim=1)
         row_w = class_weights[targets] if class_weights is not None else torch.ones_like(targets, dtype=torch.float)
         sharpened = gamma * (1.0 + 0.25 * min(1.0, n_cls / 250))
-        loss = (row_w * (1.0 - pt).pow(sharpened) * -(soft * logp).sum(dim=1)).mean()
+        loss = row_w * (1.0 - pt).pow(sharpened) * -(soft * logp).sum(dim=1)
         if n_cls > 100 and logits.requires_grad:
-            kl = F.kl_div(torch.log(probs + 1e-8), torch.full_like(probs, 1.0 / n_cls), reduction="batchmean")
-            loss = loss + min(0.12, 0.015 * (n_cls / 100)) * kl
+            kl = F.kl_div(torch.log(probs + 1e-8), torch.full_like(probs, 1.0 / n_cls), reduction="none").sum(dim=1)
+            loss = loss + min(0.12, 0.015 * (n_cls / 100)) * kl   # (batchmean = the row sums averaged over the batch)
         return loss
 
     def _class_weights(self, layer_idx: int, device) -> Optional[Tensor]:
@@ -129,19 +130,30 @@ class TagPredictionLoss(nn.Module):
 
     # -- forward ---------------------------------------------------------------------------------------------
     def forward(self, pred_logits: Tensor, target_indices: Tensor, layer_idx: int = 0):
+        """Loss and accuracy over the rows whose target is >= 0 (reference :232-321).
+
+        The reference compacts those rows with a boolean mask (`pred_logits[valid_mask]`), which costs a device -> host
+        synchronisation per level and gives every step another shape.  Here all rows go through the same fixed-shape
+        expressions and the averages are MASKED means -- same values (every term of the reference is a mean over the kept
+        rows), no synchronisation, and the whole training step can be captured in a CUDA graph.  Mixup draws its partner
+        among the kept rows, as the reference's randperm over the compacted batch does, and its Beta sample on the device."""
         keep = target_indices >= 0
-        if keep.sum() == 0:
-            zero = torch.tensor(0.0, device=pred_logits.device)
-            return zero, zero.clone()
-        logits, targets = pred_logits[keep], target_indices[keep]
-        accuracy = (logits.argmax(dim=-1) == targets).float().mean()
+        w = keep.to(pred_logits.dtype)
+        denom = w.sum().clamp(min=1.0)                 # no kept row: every masked sum is 0, like the reference's early return
+        mean = lambda per_row: (per_row * w).sum() / denom
+        logits, targets = pred_logits, target_indices.clamp(min=0)
+        accuracy = mean((logits.argmax(dim=-1) == targets).to(pred_logits.dtype))
         clean_probs = F.softmax(logits, dim=-1)
 
         mixed = self.use_mixup and logits.shape[0] > 1 and logits.requires_grad
         if mixed:
-            perm = torch.randperm(logits.shape[0], device=logits.device)
-            conc = torch.tensor(self.mixup_alpha)
-            lam = torch.distributions.Beta(conc, conc).sample().to(logits.device)
+            n, dev = logits.shape[0], logits.device
+            # a uniformly random permutation of the KEPT rows: kept rows in row order <-> kept rows in random order
+            in_order = torch.argsort((~keep).to(torch.int8), stable=True)
+            shuffled = torch.argsort(torch.rand(n, device=dev) + (~keep).to(torch.float32) * 2.0)
+            perm = torch.empty_like(in_order).scatter_(0, in_order, shuffled)
+            conc = torch.full((), float(self.mixup_alpha), device=dev)
+            lam = torch.distributions.Beta(conc, conc, validate_args=False).sample()   # (argument validation reads back to the host)
             logits = lam * logits + (1 - lam) * logits[perm]
             target_sets = ((lam, targets), (1 - lam, targets[perm]))
         else:
@@ -156,11 +168,11 @@ class TagPredictionLoss(nn.Module):
                 one = lambda t: self._focal_loss_with_weights_and_smoothing(logits, t, gamma, weights)
             else:
                 one = lambda t: self._focal_loss_with_smoothing(logits, t, gamma, alpha)
-            loss = sum(w * one(t) for w, t in target_sets)
+            loss = sum(wt * mean(one(t)) for wt, t in target_sets)
         else:
             smoothing = min(0.25, 0.05 + 0.06 * layer_idx)
-            ce = sum(w * F.cross_entropy(logits, t, reduction="mean", label_smoothing=smoothing) for w, t in target_sets)
+            ce = sum(wt * mean(F.cross_entropy(logits, t, reduction="none", label_smoothing=smoothing)) for wt, t in target_sets)
             uniform = torch.full_like(clean_probs, 1.0 / clean_probs.shape[-1])
-            kl = 0.05 * F.kl_div(torch.log(clean_probs + 1e-8), uniform, reduction="batchmean")
+            kl = 0.05 * mean(F.kl_div(torch.log(clean_probs + 1e-8), uniform, reduction="none").sum(dim=1))
             loss = ce + kl  # the reference's "L2 regulariser" iterates over the parameters of a Tensor: always 0
         return loss, accuracy

@@ -32,6 +32,7 @@ if HERE not in sys.path:
 from data.tags_processed import ItemData, RecDataset  # noqa: E402
 from hidvae_b200 import dist as hv_dist  # noqa: E402
 from hidvae_b200 import gin_lite  # noqa: E402
+from hidvae_b200.graph_step import GraphedTrainStep, step_statistics  # noqa: E402
 from modules.h_rqvae import HRqVae  # noqa: E402
 from modules.quantize import QuantizeForwardMode  # noqa: E402
 from modules.tokenizer.h_semids import HSemanticIdTokenizer  # noqa: E402
@@ -142,6 +143,8 @@ def train(
                                # `<dataset_folder>/processed/items.pt` raises unless one of the two is given
     seed=0,
     uniqueness_as_reference=True,
+    use_cuda_graph=False,      # replay the micro-step (gather + forward + backward) and the AdamW step as CUDA graphs
+                               # (hidvae_b200/graph_step.py); not with fp16 loss scaling or the Gumbel-softmax mode
 ):
     rank, world, local = hv_dist.init_from_env()
     is_main = rank == 0
@@ -209,9 +212,16 @@ def train(
             wd_i = predictor_weight_decay / (1 + 0.2 * i) if predictor_weight_decay > 0 else predictor_weight_decay
             groups.append(dict(params=list(model.tag_predictors[i].parameters()), lr=lr_i, weight_decay=wd_i))
             groups.append(dict(params=list(model.tag_projectors[i].parameters()), lr=lr_i, weight_decay=wd_i))
-        optimizer = AdamW(groups)
+        optimizer = AdamW(groups, capturable=bool(use_cuda_graph))
     else:
-        optimizer = AdamW(params=model.parameters(), lr=learning_rate, weight_decay=weight_decay)
+        optimizer = AdamW(params=model.parameters(), lr=learning_rate, weight_decay=weight_decay, capturable=bool(use_cuda_graph))
+    if use_cuda_graph:
+        if bool(amp) and mixed_precision_type == "fp16":
+            raise ValueError("train.use_cuda_graph: fp16 loss scaling reads its inf check back to the host; use bf16 or amp=False")
+        if vae_codebook_mode == QuantizeForwardMode.GUMBEL_SOFTMAX:
+            raise ValueError("train.use_cuda_graph: the Gumbel-softmax noise seed is a host scalar; use STE or ROTATION_TRICK")
+        for g_ in optimizer.param_groups:      # the graph reads the learning rate from device memory: the scheduler updates it in place
+            g_["lr"] = torch.tensor(float(g_["lr"]), device=device)
 
     start_iter = 0
     if pretrained_hrqvae_path is not None:
@@ -269,6 +279,7 @@ def train(
     t_start = time.time()
     best_eval_accuracy = 0.0
 
+    graphed = None
     for it in range(start_iter, start_iter + 1 + iterations):
         model.train()
         if it == 0 and use_kmeans_init and pretrained_hrqvae_path is None:
@@ -279,34 +290,46 @@ def train(
             if is_main:
                 logger.info("K-means initialization complete")
 
+        if use_cuda_graph and graphed is None:
+            # captured after the k-means init (it runs inside the first forward otherwise) on this rank's own sampler
+            graphed = GraphedTrainStep(model, optimizer, grads, train_dataset.__getitem__, batch_size, n_train, gumbel_t=t,
+                                       loss_divisor=gradient_accumulate_every,
+                                       autocast_dtype=torch.bfloat16 if bool(amp) else None, generator=gen)
         grads.zero()
-        out = None
-        for _ in range(gradient_accumulate_every):
-            batch = train_dataset[torch.randint(0, n_train, (batch_size,), device=device, generator=gen)]
-            with torch.autocast("cuda", dtype=torch.float16 if mixed_precision_type == "fp16" else torch.bfloat16, enabled=bool(amp)):
-                out = model(batch, gumbel_t=t)
-            scaler.scale(out.loss / gradient_accumulate_every).backward()
-        grads.all_reduce()                # (scaled) gradients first: every rank then sees the same inf / nan verdict
-        scaler.unscale_(optimizer)
-        scaler.step(optimizer)
-        scaler.update()
+        if graphed is not None:
+            for _ in range(gradient_accumulate_every):
+                stats = graphed.micro_step()
+            grads.all_reduce()
+            graphed.optimizer_step()
+            norms_dev = graphed.emb_norms
+        else:
+            out = None
+            for _ in range(gradient_accumulate_every):
+                batch = train_dataset[torch.randint(0, n_train, (batch_size,), device=device, generator=gen)]
+                with torch.autocast("cuda", dtype=torch.float16 if mixed_precision_type == "fp16" else torch.bfloat16, enabled=bool(amp)):
+                    out = model(batch, gumbel_t=t)
+                scaler.scale(out.loss / gradient_accumulate_every).backward()
+            grads.all_reduce()                # (scaled) gradients first: every rank then sees the same inf / nan verdict
+            scaler.unscale_(optimizer)
+            scaler.step(optimizer)
+            scaler.update()
+            with torch.no_grad():
+                stats = step_statistics(out)
+            norms_dev = out.embs_norm.mean(dim=0)
         if scheduler is not None:
             scheduler.step()
 
-        with torch.no_grad():
-            acc += torch.stack([out.loss.detach(), out.reconstruction_loss.mean(), out.rqvae_loss.mean(),
-                                out.tag_align_loss.mean(), out.tag_pred_loss.mean(), out.tag_pred_accuracy.mean(),
-                                out.p_unique_ids.float()])
-            acc_n += 1
+        acc += stats
+        acc_n += 1
         if is_main and it % log_every == 0:
             means = (acc / acc_n).tolist()
             acc.zero_()
             acc_n = 0
-            norms = out.embs_norm.mean(dim=0).tolist()
+            norms = norms_dev.tolist()
             rate = (it - start_iter + 1) * batch_size * gradient_accumulate_every * world / max(time.time() - t_start, 1e-9)
             history.append(dict(iter=it, **dict(zip(names, means))))
             logger.info("Iteration %d - " % it + ", ".join(f"{n}: {v:.4f}" for n, v in zip(names, means))
-                        + f", emb norms: {[round(v, 4) for v in norms]}, lr: {[g['lr'] for g in optimizer.param_groups][:2]}, "
+                        + f", emb norms: {[round(v, 4) for v in norms]}, lr: {[float(g['lr']) for g in optimizer.param_groups][:2]}, "
                         + f"items/s: {rate:.0f}")
 
         if do_eval and ((it + 1) % eval_every == 0 or it + 1 == iterations):

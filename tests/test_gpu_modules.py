@@ -319,3 +319,149 @@ train.mixed_precision_type = "fp16"
     enc_w = res["model"].encoder.mlp[0].weight
     assert enc_w.grad is not None and bool(torch.isfinite(enc_w.grad).all()) and float(enc_w.grad.abs().max()) > 0.0
     gin_lite.clear_config()
+
+
+def test_tag_prediction_loss_masked_form_equals_row_compaction(mods):
+    """TagPredictionLoss averages over the rows with a valid target without compacting them (no host synchronisation,
+    fixed shapes).  Against the reference's formulation -- boolean-mask the rows first, then plain means
+    (modules/loss.py:232-321) -- for both loss families, with and without class weights; all targets invalid gives 0."""
+    from modules.loss import TagPredictionLoss
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    n, c = 257, 140
+    logits = torch.randn(n, c, generator=g).cuda().requires_grad_(True)
+    targets = torch.randint(0, c, (n,), generator=g)
+    targets[::7] = -1
+    targets = targets.cuda()
+    keep = targets >= 0
+    for focal, counts in ((False, None), (True, None), (True, {1: torch.randint(1, 50, (c,), generator=g).cuda()})):
+        crit = TagPredictionLoss(use_focal_loss=focal, focal_params={"gamma": 2.2, "alpha": 0.3}, class_counts=counts)
+        crit.use_mixup = False
+        loss, acc = crit(logits, targets, layer_idx=1)
+        # reference formulation on the compacted rows (every helper returns one value per row)
+        lk, tk = logits[keep], targets[keep]
+        if not focal:
+            s = min(0.25, 0.05 + 0.06 * 1)
+            probs = F.softmax(lk, dim=-1)
+            ref = F.cross_entropy(lk, tk, label_smoothing=s) + 0.05 * F.kl_div(torch.log(probs + 1e-8), torch.full_like(probs, 1.0 / c),
+                                                                                 reduction="batchmean")
+        elif counts is None:
+            ref = crit._focal_loss_with_smoothing(lk, tk, 2.2 * 1.35, max(0.08, 0.3 - 0.06)).mean()
+        else:
+            ref = crit._focal_loss_with_weights_and_smoothing(lk, tk, 2.2 * 1.35, crit._class_weights(1, lk.device)).mean()
+        torch.testing.assert_close(loss, ref, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(acc, (lk.argmax(-1) == tk).float().mean(), rtol=0, atol=1e-6)
+        (gl,) = torch.autograd.grad(loss, logits, retain_graph=True)
+        (gr,) = torch.autograd.grad(ref, logits)
+        torch.testing.assert_close(gl, gr, rtol=1e-4, atol=1e-7)
+        assert float(gl[~keep].abs().max()) == 0.0                 # dropped rows receive no gradient
+    none_valid = torch.full((n,), -1, device="cuda")
+    loss0, acc0 = crit(logits, none_valid)
+    assert float(loss0) == 0.0 and float(acc0) == 0.0
+    # mixup: partners are drawn among the kept rows only, so the loss stays finite and dropped rows stay gradient-free
+    crit.use_mixup = True
+    torch.manual_seed(1)
+    loss_m, _ = crit(logits, targets, layer_idx=1)
+    (gm,) = torch.autograd.grad(loss_m, logits)
+    assert bool(torch.isfinite(loss_m)) and float(gm[~keep].abs().max()) == 0.0 and float(gm[keep].abs().max()) > 0.0
+
+
+def _small_tagged_model(mods):
+    torch.manual_seed(0)
+    np.random.seed(0)
+    m = mods.HRqVae(input_dim=64, embed_dim=32, hidden_dims=[48], codebook_size=64, codebook_kmeans_init=False,
+                    codebook_normalize=True, codebook_mode=mods.QuantizeForwardMode.ROTATION_TRICK, n_layers=3, n_cat_features=0,
+                    commitment_weight=0.4, tag_class_counts=[5, 9, 17], tag_embed_dim=24, dropout_rate=0.0,
+                    sem_id_uniqueness_weight=0.5, sem_id_uniqueness_margin=0.2).cuda().train()
+    m.tag_prediction_loss.use_mixup = False
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return m
+
+
+def test_graphed_train_step_equals_eager_steps(mods):
+    """hidvae_b200.graph_step.GraphedTrainStep (gather + forward + backward as one CUDA graph, AdamW as another) against
+    the same number of eager steps on the same index draws: parameters agree to summation-order noise, statistics too."""
+    from data.schemas import TaggedSeqBatch
+    from hidvae_b200 import dist as hv_dist
+    from hidvae_b200.graph_step import GraphedTrainStep, step_statistics
+    n, bs, steps, warm = 4096, 256, 6, 3
+    g = torch.Generator().manual_seed(3)
+    x = unit_rows(n, 64, 1).cuda()
+    tags_emb = torch.randn(n, 3, 24, generator=g).cuda()
+    tags_idx = torch.stack([torch.randint(0, c, (n,), generator=g) for c in (5, 9, 17)], dim=1)
+    tags_idx[::9, 2] = -1
+    tags_idx = tags_idx.cuda()
+    fetch = lambda idx: TaggedSeqBatch(None, None, None, x[idx], None, None, tags_emb[idx], tags_idx[idx])
+    results = []
+    for graphed in (False, True):
+        model = _small_tagged_model(mods)
+        grads = hv_dist.FlatGradAllReduce(model.parameters())
+        opt = torch.optim.AdamW(model.parameters(), lr=torch.tensor(1e-3, device="cuda"), weight_decay=0.01, capturable=True)
+        gen = torch.Generator(device="cuda").manual_seed(11)
+        stats = None
+        if graphed:
+            step = GraphedTrainStep(model, opt, grads, fetch, bs, n, gumbel_t=0.2, generator=gen, warmup=warm)
+            for _ in range(steps):
+                stats = step().clone()
+        else:
+            for _ in range(warm + steps):
+                idx = torch.randint(0, n, (bs,), device="cuda", generator=gen)
+                grads.zero()
+                out = model(fetch(idx), gumbel_t=0.2)
+                out.loss.backward()
+                opt.step()
+                stats = step_statistics(out)
+        results.append((torch.cat([p.detach().flatten() for p in model.parameters()]), stats))
+    (p_e, s_e), (p_g, s_g) = results
+    torch.testing.assert_close(s_g, s_e, rtol=2e-3, atol=2e-4)
+    assert float((p_g - p_e).abs().max()) < 5e-4                  # nine Adam steps of 1e-3 each: the two runs stay together
+    with pytest.raises(ValueError, match="capturable"):
+        GraphedTrainStep(model, torch.optim.AdamW(model.parameters(), lr=1e-3), grads, fetch, bs, n)
+
+
+def test_trainer_with_cuda_graph(mods, tmp_path):
+    """train_hidvae.train(use_cuda_graph=True): k-means init, then graph replays with the cosine schedule writing the
+    learning rate in place; the RQ loss must fall as in the eager run, evaluation runs between replays."""
+    from hidvae_b200 import gin_lite
+    import train_hidvae
+    gin_lite.clear_config()
+    gin_lite.parse_config("""
+import modules.quantize
+train.iterations = 60
+train.batch_size = 128
+train.gradient_accumulate_every = 2
+train.vae_input_dim = 768
+train.vae_n_cat_feats = 0
+train.vae_hidden_dims = [128, 64]
+train.vae_embed_dim = 32
+train.vae_codebook_size = 64
+train.vae_codebook_normalize = True
+train.vae_n_layers = 3
+train.vae_codebook_mode = %modules.quantize.QuantizeForwardMode.ROTATION_TRICK
+train.dataset = %data.tags_processed.RecDataset.AMAZON
+train.commitment_weight = 0.4
+train.tag_class_counts = [8, 16, 32]
+train.tag_embed_dim = 768
+train.layer_specific_lr = True
+train.learning_rate = 0.001
+train.lr_scheduler_T_max = 60
+train.eval_every = 30
+train.use_kmeans_init = True
+train.synthetic_items = 3000
+train.log_every = 10
+train.use_cuda_graph = True
+""")
+    res = train_hidvae.train(save_dir_root=str(tmp_path), dataset_folder="")
+    logs = [h for h in res["history"] if "eval" not in h]
+    evals = [h["eval"] for h in res["history"] if "eval" in h]
+    assert len(logs) >= 6 and len(evals) == 2
+    assert all(np.isfinite(h["loss"]) for h in logs)
+    assert logs[-1]["rqvae"] < logs[0]["rqvae"] * 1.05
+    assert 0.0 <= evals[-1]["sem_id_repetition_rate"] <= 1.0 and evals[-1]["codebook_usage_0"] > 0.3
+    gin_lite.clear_config()
+    gin_lite.parse_config("train.use_cuda_graph = True\ntrain.amp = True\ntrain.synthetic_items = 500\ntrain.dataset = %data.tags_processed.RecDataset.AMAZON\n")
+    with pytest.raises(ValueError, match="fp16"):
+        train_hidvae.train(save_dir_root=str(tmp_path), dataset_folder="")
+    gin_lite.clear_config()
