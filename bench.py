@@ -396,8 +396,11 @@ def run_train_dp(rank, world, dev):
         res["codebooks_identical_on_all_ranks"] = bool(same.item())
 
     grads = hv_dist.FlatGradAllReduce(model.parameters())
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
     res["flat_gradient_bytes"] = grads.flat.numel() * 4
+    res["matmul_precision"] = "tf32 (torch.set_float32_matmul_precision('high'), as the reference sets at modules/h_rqvae.py:21)"
+    precision_before = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("high")
 
     if world > 1:   # the one-kernel peer-memory exchange against NCCL on the same data
         try:
@@ -421,7 +424,7 @@ def run_train_dp(rank, world, dev):
 
     from hidvae_b200.graph_step import GraphedTrainStep
     fetch = lambda idx: TaggedSeqBatch(None, None, None, x[idx], None, None, tags_emb[idx], tags_idx[idx])
-    opt_g = torch.optim.AdamW(model.parameters(), lr=torch.tensor(1e-4, device=dev), weight_decay=0.01, capturable=True)
+    opt_g = torch.optim.AdamW(model.parameters(), lr=torch.tensor(1e-4, device=dev), weight_decay=0.01, capturable=True, fused=True)
 
     def timed(fn, reps):
         if world > 1:
@@ -447,11 +450,12 @@ def run_train_dp(rank, world, dev):
             out.loss.backward()
             grads.all_reduce()
             opt.step()
-            last["loss"] = out.loss
+            last["loss"] = out.loss.detach()   # (a live autograd graph would pin AccumulateGrad nodes to this stream)
 
         for _ in range(5):
             step()
         eager_ms = timed(step, 20)
+        last.clear()
         # the same step as two CUDA-graph replays around the NCCL exchange (hidvae_b200/graph_step.py)
         graphed = GraphedTrainStep(model, opt_g, grads, fetch, bs, n_items, gumbel_t=0.2, generator=g, warmup=3)
         for _ in range(3):
@@ -464,6 +468,7 @@ def run_train_dp(rank, world, dev):
                                            loss=float(graphed.stats[0]), step="CUDA graphs: gather + forward + backward | NCCL "
                                            "all-reduce of the flat gradient | AdamW")
         del graphed
+    torch.set_float32_matmul_precision(precision_before)
     return res
 
 

@@ -380,10 +380,11 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
         const uint32_t tk = *reinterpret_cast<volatile uint32_t*>(&s_tk[4 * wg + 2 * (lvl & 1) + u]), acc = tk % kAccs, use = tk / kAccs;
         ptx::mbar_wait(ptx::smem_u32(&bar_mma_done[acc]), use & 1u);
         ptx::tc_fence_after_sync();
-        if (u == 0) stamp(5);
+        stamp(u == 0 ? 5 : 9);
         float m;
         int c;
         scan_unit(tmem_base + acc * kUnitCols + lane_bits, m, c);
+        if (u == 0) stamp(8);
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::counter_add_release(ptx::smem_u32(&s_free[acc]), 1u);

@@ -56,6 +56,32 @@ __device__ __forceinline__ float pair_cos(const UniqArgs& a, int64_t i, int64_t 
   return ij * (*inv_i) * (*inv_j);
 }
 
+// Keys of rows [row0, row0 + kTile) into s_keys (every thread of the CTA calls it; rows past the end get 0).  Narrow rows:
+// a thread per row.  Wide rows (the as-wired transposed call of the reference hands over [L, B]: 3 rows of B ids): a warp
+// per row, lanes striding the columns, lane hashes combined order-independently -- a row of 8,192 ids is 256 loads per lane
+// instead of a serial chain of 8,192.  Any deterministic function of the row's content serves as a key: equal keys are
+// always confirmed element by element.
+__device__ __forceinline__ void tile_keys(const UniqArgs& a, int64_t row0, uint64_t* s_keys) {
+  if (a.width <= 64) {
+    const int64_t r = row0 + threadIdx.x;
+    s_keys[threadIdx.x] = r < a.rows ? row_key(a, r) : 0ull;
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < kTile; t += kTile / 32) {
+    const int64_t r = row0 + t;
+    uint64_t h = 0ull;
+    if (r < a.rows) {
+      h = 0x243F6A8885A308D3ull + static_cast<uint64_t>(lane);
+      for (int64_t c = lane; c < a.width; c += 32) h = mix64(h, static_cast<uint64_t>(a.ids[r * a.row_stride + c * a.col_stride]));
+      h = mix64(h, static_cast<uint64_t>(lane) + 1ull);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, off);
+    }
+    if (lane == 0) s_keys[t] = h;
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ T block_sum(T v, T* scratch) {
 #pragma unroll
@@ -80,21 +106,25 @@ __global__ void __launch_bounds__(kTile) uniq_kernel(UniqArgs a, double* __restr
 
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kTile + threadIdx.x;
   const bool valid_i = i < a.rows;
-  const uint64_t my_key = valid_i ? row_key(a, i) : 0ull;
   const int64_t n_tiles = (a.rows + kTile - 1) / kTile;
 
   float coef = 0.f;
   if (BACKWARD) {
     const double pairs = stats_in[1];
-    coef = pairs > 0.0 ? static_cast<float>(static_cast<double>(g_out[0]) * weight / pairs) : 0.f;
+    if (!(pairs > 0.0)) return;  // no identical pair in the batch (uniform across the grid): the gradient is zero
+    coef = static_cast<float>(static_cast<double>(g_out[0]) * weight / pairs);
   }
+  tile_keys(a, static_cast<int64_t>(blockIdx.x) * kTile, s_keys);
+  __syncthreads();
+  const uint64_t my_key = s_keys[threadIdx.x];
 
   double hinge_sum = 0.0, pair_count = 0.0, has_later = 0.0;
   for (int64_t jt = blockIdx.x; jt < n_tiles; ++jt) {
-    const int64_t j_load = jt * kTile + threadIdx.x;
-    __syncthreads();
-    s_keys[threadIdx.x] = j_load < a.rows ? row_key(a, j_load) : 0ull;
-    __syncthreads();
+    if (jt > blockIdx.x) {  // (the first tile of the sweep is the CTA's own: its keys are in place)
+      __syncthreads();
+      tile_keys(a, jt * kTile, s_keys);
+      __syncthreads();
+    }
     if (!valid_i) continue;
     const int64_t j0 = jt * kTile;
     const int j_end = static_cast<int>(a.rows - j0 < kTile ? a.rows - j0 : kTile);
@@ -151,7 +181,8 @@ __global__ void __launch_bounds__(kTile) uniq_sorted_kernel(UniqArgs a, const ui
   float coef = 0.f;
   if (BACKWARD) {
     const double pairs = stats_in[1];
-    coef = pairs > 0.0 ? static_cast<float>(static_cast<double>(g_out[0]) * weight / pairs) : 0.f;
+    if (!(pairs > 0.0)) return;  // no identical pair: zero gradient
+    coef = static_cast<float>(static_cast<double>(g_out[0]) * weight / pairs);
   }
   double hinge_sum = 0.0, pair_count = 0.0, has_later = 0.0;
   if (p < a.rows) {

@@ -15,7 +15,9 @@ replays are back to back.  Requirements, checked at construction: no fp16 loss s
 host), a model whose forward is free of host synchronisation (HRqVae is: the tag losses are masked fixed-shape means, the
 uniqueness loss and p_unique_ids are kernels), fixed batch size, STE / rotation-trick quantiser (the Gumbel-softmax kernels
 take their noise seed as a host scalar, which a graph would freeze: `ops.gumbel_apply` refuses to be captured).  Dropout and
-mixup draws advance inside the graph through PyTorch's graph-safe Philox offsets.  The warm-up steps are REAL optimisation
+mixup draws advance inside the graph through PyTorch's graph-safe Philox offsets.  No autograd graph of an EARLIER eager
+step may still be alive when this is built (e.g. a kept `out.loss`): its AccumulateGrad nodes are bound to the stream they
+ran on, and the capture would have to synchronise with it.  The warm-up steps are REAL optimisation
 steps (with the gradient exchange): a run with `warmup` = 3 has made three steps when the constructor returns."""
 from typing import Callable, Optional
 
