@@ -285,7 +285,7 @@ class HRqVae(nn.Module, _HubMixin):
             return emb, res, ids, loss
         res = encoded_x
         embs, residuals, ids = [], [], []
-        loss = torch.tensor(0.0, device=encoded_x.device)
+        loss = torch.zeros((), device=encoded_x.device)
         for layer in self.layers:
             residuals.append(res)
             q = layer(res, temperature=gumbel_t)

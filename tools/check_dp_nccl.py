@@ -1,5 +1,6 @@
 """torchrun check of the data-parallel paths on real GPUs (NCCL): sharded k-means == single-process k-means, the flat
-gradient all-reduce, item-sharded bulk assignment + final gather, and a few iterations of the gin-configured trainer.
+gradient all-reduce, item-sharded bulk assignment + final gather, and a few iterations of the gin-configured trainer, eager
+and as CUDA graphs (gather + forward + backward | NCCL all-reduce | AdamW).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_dp_nccl.py
 Prints one JSON line {"ok": true, ...} on rank 0.
@@ -94,14 +95,15 @@ train.tag_class_counts = [37, 168, 353]
 train.dataset_folder = "{tmp}/data"
 train.save_dir_root = "{tmp}/out"
 """)
-    out = train_hidvae.train()
-flat = torch.cat([p.detach().reshape(-1) for p in out["model"].parameters()])
-ref = flat.clone()
-dist.broadcast(ref, src=0)
-assert torch.equal(flat, ref), "ranks hold different parameters after data-parallel training"
-losses = [h["loss"] for h in out["history"] if "loss" in h]
-assert all(np.isfinite(losses)), losses
-report["trainer_losses"] = losses
+    for graphed in (False, True):   # (5) the same run with the step replayed as CUDA graphs around the NCCL exchange
+        out = train_hidvae.train(use_cuda_graph=graphed)
+        flat = torch.cat([p.detach().reshape(-1) for p in out["model"].parameters()])
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(flat, ref), f"ranks hold different parameters after data-parallel training (cuda graph: {graphed})"
+        losses = [h["loss"] for h in out["history"] if "loss" in h]
+        assert all(np.isfinite(losses)), losses
+        report["trainer_losses_graphed" if graphed else "trainer_losses"] = losses
 
 dist.barrier()
 if rank == 0:
