@@ -558,8 +558,19 @@ def run_sweep(ops, pk, dev):
         model(batch, gumbel_t=0.2).loss.backward()
 
     t_c1 = mean(c1_step, 30, flush)
-    res.append(dict(case="c1_HRqVae.forward+backward_batch1024_untagged (module API, eager PyTorch MLPs + fused RQ)", n=1024,
-                    ms=t_c1, items_per_s=1024 / (t_c1 * 1e-3)))
+    # the same forward + backward replayed as one CUDA graph (gradients accumulate into static buffers, as the trainer's
+    # GraphedTrainStep does): what the launch-bound eager number hides
+    for p_ in model.parameters():
+        p_.grad = torch.zeros_like(p_)
+    torch.cuda.synchronize()
+
+    def c1_fwd_bwd():
+        model(batch, gumbel_t=0.2).loss.backward()
+
+    c1_graph = GraphedStep(c1_fwd_bwd)
+    t_c1g = mean(c1_graph, 50, flush)
+    res.append(dict(case="c1_HRqVae.forward+backward_batch1024_untagged (module API: PyTorch MLPs + fused RQ)", n=1024,
+                    ms=t_c1g, items_per_s=1024 / (t_c1g * 1e-3), eager_ms=t_c1, note="ms = one CUDA-graph replay, eager_ms = eager PyTorch"))
     return res
 
 
