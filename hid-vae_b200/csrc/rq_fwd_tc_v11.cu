@@ -23,7 +23,7 @@
 //              (unit number % 3) as soon as its previous user has been scanned.  The scan of unit 0 overlaps the MMAs
 //              of unit 1 and of other tiles, and no scanning warp ever waits inside an issue loop (which, with the
 //              owners issuing for themselves, held accumulators hostage: measured 9000 cycles per level).
-//   SCAN       by the row's owner: 2-D fold with 3-input maxima over 16-column loads (rq_fwd_tc_v10.cu), exact
+//   SCAN       by the row's owner: 2-D fold with 3-input maxima over 16-column loads, exact
 //              first-index path when a row has more than one maximiser; the id stays in a register.
 //   score[row, k] = r.c_k - |c_k|^2 / 2 with the bf16 3-way split exactly as in the other generations
 //   (modules/quantize.py:108-122); only ids (and emb_out / loss in training) leave the SM.
@@ -58,7 +58,7 @@ constexpr int kTmemCols = 512;  // 3 x 128 accumulator columns + 4 x 32 A column
 constexpr int kMaxLevels = 3;
 constexpr int kOnesBytes = 2 * kTileRows * 16;
 constexpr int kBarBytes = 1024;
-constexpr int kImageBytes = kNTile * (4 * D + 32);  // packed bf16 image of one level (rq_fwd_tc.cu)
+constexpr int kImageBytes = kNTile * (4 * D + 32);  // packed bf16 image of one level (rq_pack.cu)
 constexpr int kCbBytes = kNTile * D * 4;            // swizzled fp32 codebook of one level
 constexpr int kSmemLimit = 227 * 1024;
 #ifdef HV_TC_INSTRUMENT

@@ -48,7 +48,7 @@ struct TcPlan {
 };
 
 bool plan_for(int d, int k, int n_levels, int n_wg, TcPlan* p) {
-  p->ntile = 256;  // image format of rq_fwd_tc.cu: every N tile holds 256 codes (padded codes can never win)
+  p->ntile = 256;  // image format of rq_pack.cu: every N tile holds 256 codes (padded codes can never win)
   p->n_ktiles = (k + p->ntile - 1) / p->ntile;
   p->tile_bytes = p->ntile * (4 * d + 32);
   p->a_bytes = kTileRows * d * 4;
