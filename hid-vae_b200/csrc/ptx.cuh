@@ -249,6 +249,34 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
                :
                : "memory");
 }
+// 32 lanes x 8 consecutive fp32 columns (the small shape lets a thread keep two loads in flight in 16 registers)
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// wait for every outstanding tcgen05.ld of the thread; the registers of the load(s) that must be complete are tied to the
+// asm so that no use of them is scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t (&v)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t (&v)[8], uint32_t (&w)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(w[0]),
+                 "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7])
+               :
+               : "memory");
+}
+// registers -> tensor memory: 8 consecutive 32-bit columns of the thread's own lane
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 // registers -> tensor memory: thread i of the warp writes row (lane_base + i), 16 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(

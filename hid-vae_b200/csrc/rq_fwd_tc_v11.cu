@@ -29,16 +29,13 @@
 //   (modules/quantize.py:108-122); only ids (and emb_out / loss in training) leave the SM.
 #include <stdlib.h>
 
-#include "common.cuh"
-#include "ptx.cuh"
+#include "rq_rows.cuh"
 
 namespace hv {
 namespace {
 
-constexpr int D = 32;
-constexpr int kTileRows = 128;
-constexpr int kNTile = 256;   // codes per operand image
-constexpr int kUnitCols = 128;
+using namespace rows;
+
 #ifndef HV_V11_WGS
 #define HV_V11_WGS 3  // measured: three owners at 128 registers beat four at 112 (spills)
 #endif
@@ -52,120 +49,20 @@ constexpr int kThreads = (kWGs + 1) * 128;  // (register allocation is per warpg
 constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8;
 constexpr int kOwnerRegs = kWGs == 4 ? 112 : HV_V11_OWNER_REGS, kIssuerRegs = kWGs == 4 ? 24 : (HV_V11_OWNER_REGS > 128 ? 24 : 128);
 static_assert(kWGs * 128 * kOwnerRegs + 128 * kIssuerRegs <= kThreads * kLaunchRegs, "register hand-over must stay inside the launch allocation");
-constexpr int kQueue = 8;               // staged (warpgroup, level) requests waiting for the issuer
-constexpr int kAccs = 3;
 constexpr int kTmemCols = 512;  // 3 x 128 accumulator columns + 4 x 32 A columns
-constexpr int kMaxLevels = 3;
-constexpr int kOnesBytes = 2 * kTileRows * 16;
-constexpr int kBarBytes = 1024;
-constexpr int kImageBytes = kNTile * (4 * D + 32);  // packed bf16 image of one level (rq_pack.cu)
-constexpr int kCbBytes = kNTile * D * 4;            // swizzled fp32 codebook of one level
-constexpr int kSmemLimit = 227 * 1024;
 #ifdef HV_TC_INSTRUMENT
 constexpr bool kInstr = true;
 #else
 constexpr bool kInstr = false;
 #endif
 
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // FMNMX3
-  return d;
-}
-__device__ __forceinline__ float f(uint32_t v) { return __uint_as_float(v); }
-__device__ __forceinline__ float max16(const uint32_t (&v)[16]) {
-  const float a0 = max3(f(v[0]), f(v[1]), f(v[2])), a1 = max3(f(v[3]), f(v[4]), f(v[5]));
-  const float a2 = max3(f(v[6]), f(v[7]), f(v[8])), a3 = max3(f(v[9]), f(v[10]), f(v[11]));
-  const float a4 = max3(f(v[12]), f(v[13]), f(v[14]));
-  return fmaxf(max3(a0, a1, a2), max3(a3, a4, f(v[15])));
-}
-constexpr float kBig = 1.329227995784916e36f;  // 2^120
-
-// Exact first-index (max, argmax) of one 16-column chunk against the running pair (slow path).
-__device__ __forceinline__ void scan_chunk_exact(const uint32_t (&v)[16], int base, float& best, int& best_col) {
-  const float m = max16(v);
-  if (m > best) {  // strict: an earlier chunk keeps exact ties
-    float t = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) t = fmaxf(t, fmaf(f(v[j]) - m, kBig, static_cast<float>(16 - j)));
-    best = m;
-    best_col = base + 16 - static_cast<int>(t);
-  }
-}
-
-// Scan of this thread's row over the 128 columns of one accumulator at TMEM address `t0`: maximum and first column.
+// Scan of this thread's row over the 128 columns of one accumulator (rq_rows.cuh); -DHV_V11_SCAN=0: the unpipelined 16-column form
 __device__ __forceinline__ void scan_unit(uint32_t t0, float& m_out, int& col_out) {
-  float g[16], cm[8];
-  uint32_t a[16], b[16];
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    ptx::tmem_ld_32x16(t0 + 32 * p, a);
-    ptx::tmem_ld_32x16(t0 + 32 * p + 16, b);
-    ptx::tmem_wait_ld(a, b);
-    cm[2 * p] = max16(a);
-    cm[2 * p + 1] = max16(b);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) g[j] = p == 0 ? fmaxf(f(a[j]), f(b[j])) : max3(g[j], f(a[j]), f(b[j]));
-  }
-  const float m = max3(max3(cm[0], cm[1], cm[2]), max3(cm[3], cm[4], cm[5]), fmaxf(cm[6], cm[7]));
-  // class of the maximiser: sum_j [g_j == m] * (32 + j);  chunk: sum_c [cm_c == m] * (16 + c)   (FMA pipe)
-  float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float e = __saturatef(fmaf(g[j] - m, kBig, 1.0f));
-    s4[j & 3] = fmaf(e, static_cast<float>(32 + j), s4[j & 3]);
-  }
-  float c2[2] = {0.f, 0.f};
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float e = __saturatef(fmaf(cm[c] - m, kBig, 1.0f));
-    c2[c & 1] = fmaf(e, static_cast<float>(16 + c), c2[c & 1]);
-  }
-  const float cls = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-  const float chk = c2[0] + c2[1];
-  // exactly one class and one chunk attain m (all-padding units, m = -1e30, cannot win anyway; NaN takes the exact path)
-  const bool unique = (cls < 64.f && chk < 32.f) || m < -1e29f;
-  float best = m;
-  int col = 16 * (static_cast<int>(chk) - 16) + static_cast<int>(cls) - 32;
-  if (__any_sync(0xffffffffu, !unique)) {
-    best = -INFINITY;
-    col = 0;
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      ptx::tmem_ld_32x16(t0 + 16 * c, a);
-      ptx::tmem_wait_ld16(a);
-      scan_chunk_exact(a, 16 * c, best, col);
-    }
-  }
-  m_out = best;
-  col_out = col;
-}
-
-// One unit (128 codes starting at code `col0` of the level's image): 3*D/16 MMAs with A from tensor memory, the norm
-// MMA with the constant ones block from shared memory, one commit.  Called by ONE elected thread.
-__device__ __forceinline__ void issue_unit(uint32_t acc, uint32_t a_tmem, uint32_t ones, uint32_t b_tile, int col0,
-                                           uint32_t bar_done) {
-  constexpr uint32_t idesc = ptx::umma_idesc_bf16(kTileRows, kUnitCols);
-  const uint32_t hi = ptx::umma_desc_hi(128);
-  constexpr uint32_t chunk_b = kNTile * 16;  // bytes between K chunks of the B image
-  constexpr uint32_t b_step = 2 * kNTile;    // one K=16 step = two chunks, in 16-byte units
-  const uint32_t b_hi = b_tile + col0 * 16;
-  const uint32_t d_bhi = ptx::umma_desc_lo(b_hi, chunk_b);
-  const uint32_t d_blo = ptx::umma_desc_lo(b_hi + (D / 8) * chunk_b, chunk_b);
-  const uint32_t d_bnrm = ptx::umma_desc_lo(b_hi + 2 * (D / 8) * chunk_b, chunk_b);
-  const uint32_t d_one = ptx::umma_desc_lo(ones, kTileRows * 16);
-  const uint32_t a_hi = a_tmem, a_lo = a_tmem + D / 2;  // D/2 columns each: two bf16 per column
-#pragma unroll
-  for (int j = 0; j < D / 16; ++j)  // r_hi . c_hi
-    ptx::umma_bf16_ts(acc, a_hi + 8 * j, ptx::umma_desc(d_bhi + j * b_step, hi), idesc, j > 0 ? 1u : 0u);
-#pragma unroll
-  for (int j = 0; j < D / 16; ++j)  // r_lo . c_hi
-    ptx::umma_bf16_ts(acc, a_lo + 8 * j, ptx::umma_desc(d_bhi + j * b_step, hi), idesc, 1u);
-#pragma unroll
-  for (int j = 0; j < D / 16; ++j)  // r_hi . c_lo
-    ptx::umma_bf16_ts(acc, a_hi + 8 * j, ptx::umma_desc(d_blo + j * b_step, hi), idesc, 1u);
-  ptx::umma_bf16(acc, ptx::umma_desc(d_one, hi), ptx::umma_desc(d_bnrm, hi), idesc, 1u);  // 1 * (-|c|^2 / 2)
-  ptx::umma_commit(bar_done);
+#if defined(HV_V11_SCAN) && HV_V11_SCAN == 0
+  scan_unit_x16(t0, m_out, col_out);
+#else
+  scan_unit_x8_pairs(t0, m_out, col_out);
+#endif
 }
 
 struct V11Params {
@@ -185,15 +82,15 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
   uint8_t* s_cb = s_img + a.n_levels * kImageBytes;
 
   uint64_t* bar_b_full = s_bar;                      // [kMaxLevels]  TMA -> everybody (images + codebooks of a level)
-  uint64_t* bar_mma_done = bar_b_full + kMaxLevels;  // [kAccs]  MMA completion -> the owning warpgroup
-  // Progress COUNTERS, not phase parities: with two tickets per warpgroup up to eight tickets are outstanding, so a
-  // waiter can be two uses of an accumulator ahead of its barrier, where a parity test would pass too early.
-  uint32_t* s_free = reinterpret_cast<uint32_t*>(bar_mma_done + kAccs);  // [kAccs]  warps that finished scanning it
-  uint32_t* s_issued = s_free + kAccs;               // [kWGs]   units of the warpgroup the issuer has committed
-  uint32_t* s_qtail = s_issued + kWGs;               // requests pushed so far
+  // Every wait of an owner is a hardware-parked mbarrier wait (polled progress counters were 15 % of the issued
+  // instructions).  A (warpgroup, unit) barrier completes once per level of the warpgroup, in order, so its parity is
+  // exact; an accumulator's "scanned" barrier has one waiter (the issuer) that never skips a phase.
+  uint64_t* bar_done = bar_b_full + kMaxLevels;      // [kWGs][2]  unit of the warpgroup's level committed (issuer + MMA completion)
+  uint64_t* bar_free = bar_done + 2 * kWGs;          // [kAccs]  the four warps of the owner have scanned the accumulator
+  uint32_t* s_qtail = reinterpret_cast<uint32_t*>(bar_free + kAccs);  // requests pushed so far
   uint32_t* s_q = s_qtail + 1;                       // [kQueue] (sequence + 1) << 8 | level << 4 | warpgroup
-  uint32_t* s_tk = s_q + kQueue;                     // [kWGs][2][2]  unit numbers of the warpgroup's level (double-buffered)
-  uint32_t* s_tmem = s_tk + 4 * kWGs;
+  uint32_t* s_tk = s_q + kQueue;                     // [kWGs][2]  accumulator of the warpgroup's unit (published by the issuer's arrive)
+  uint32_t* s_tmem = s_tk + 2 * kWGs;
   uint32_t* s_ts = s_tmem + 1;                       // [192] timestamps of block 0, warpgroup 0 (instrumented builds)
 
   const int warp = threadIdx.x >> 5;
@@ -214,11 +111,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxLevels; ++i) ptx::mbar_init(ptx::smem_u32(&bar_b_full[i]), 1);
-    for (int i = 0; i < kAccs; ++i) {
-      ptx::mbar_init(ptx::smem_u32(&bar_mma_done[i]), 1);
-      s_free[i] = 0;
-    }
-    for (int i = 0; i < kWGs; ++i) s_issued[i] = 0;
+    for (int i = 0; i < 2 * kWGs; ++i) ptx::mbar_init(ptx::smem_u32(&bar_done[i]), 2);
+    for (int i = 0; i < kAccs; ++i) ptx::mbar_init(ptx::smem_u32(&bar_free[i]), 4);
     for (int i = 0; i < kQueue; ++i) s_q[i] = 0;
     *s_qtail = 0;
     ptx::fence_mbar_init();
@@ -234,11 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
     ptx::tmem_relinquish();
   }
   if (threadIdx.x >= 128 && threadIdx.x < 128 + kTileRows) {
-    // constant A block that multiplies the norm pieces: row -> [1, 1, 1, 0, 0, 0, 0, 0 | 0 x 8]
-    const int i = threadIdx.x - 128;
-    *reinterpret_cast<uint4*>(s_ones + i * 16) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
-    *reinterpret_cast<uint4*>(s_ones + kTileRows * 16 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
-    ptx::fence_proxy_async_smem();
+    write_ones_block(s_ones, threadIdx.x - 128);
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -266,13 +156,14 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
       const uint32_t n_req = static_cast<uint32_t>(my_tiles) * static_cast<uint32_t>(n_levels);
       uint32_t unit = 0;  // units issued so far: accumulator = unit % 3, its use number = unit / 3
       auto issue = [&](uint32_t rwg, uint32_t l, uint32_t u) {
-        s_tk[4 * rwg + 2 * ((s_issued[rwg] >> 1) & 1u) + u] = unit;  // (only this thread writes s_issued: a plain read is exact)
         const uint32_t acc = unit % kAccs, use = unit / kAccs;
-        ptx::counter_wait(ptx::smem_u32(&s_free[acc]), 4u * use);  // every earlier use of the accumulator is scanned
+        if (use > 0) ptx::mbar_wait(ptx::smem_u32(&bar_free[acc]), (use - 1u) & 1u);  // every earlier use of the accumulator is scanned
         ptx::tc_fence_after_sync();
+        s_tk[2 * rwg + u] = acc;
+        const uint32_t bar = ptx::smem_u32(&bar_done[2 * rwg + u]);
         issue_unit(tmem_base + acc * kUnitCols, tmem_base + kAccs * kUnitCols + rwg * D, ones, ptx::smem_u32(s_img + l * kImageBytes),
-                   u * kUnitCols, ptx::smem_u32(&bar_mma_done[acc]));
-        ptx::counter_add_release(ptx::smem_u32(&s_issued[rwg]), 1u);
+                   u * kUnitCols, bar);
+        ptx::mbar_arrive(bar);  // (release: publishes s_tk; the phase completes with the MMAs' own arrival)
         ++unit;
       };
       bool have_pending = false;
@@ -297,7 +188,11 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
         if (s < static_cast<uint32_t>(kWGs * n_levels)) ptx::mbar_wait(ptx::smem_u32(&bar_b_full[l]), 0u);  // images are loaded once
         issue(rwg, l, 0u);
         if (have_pending) issue(pend_wg, pend_l, 1u);
+#ifdef HV_V11_NO_DEFER
+        issue(rwg, l, 1u);
+#else
         have_pending = true, pend_wg = rwg, pend_l = l;
+#endif
       }
       if (have_pending) issue(pend_wg, pend_l, 1u);
     }
@@ -316,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
   };
 
   bool have_x = false;
-  uint32_t lvl = 0;  // levels done by this warpgroup (selects the s_tk buffer)
+  uint32_t lvl = 0;  // levels done by this warpgroup (parity of its unit barriers)
   for (int i = wg; i < my_tiles; i += kWGs) {
     const int64_t grow = tile_row0(i) + t;
     const bool valid = grow < a.n;
@@ -341,15 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
       {
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float x0 = r[2 * j], x1 = r[2 * j + 1];
-          const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-          const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hh);
-          const float h0 = __uint_as_float(hw << 16), h1 = __uint_as_float(hw & 0xFFFF0000u);
-          const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - h0, x1 - h1);
-          hi[j] = hw;
-          lo[j] = *reinterpret_cast<const uint32_t*>(&ll);
-        }
+        for (int j = 0; j < 16; ++j) split_pair(r[2 * j], r[2 * j + 1], hi[j], lo[j]);
         ptx::tmem_st_32x16(a_tmem + lane_bits, hi);
         ptx::tmem_st_32x16(a_tmem + lane_bits + 16, lo);
         ptx::tmem_wait_st();
@@ -375,10 +262,8 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
       int col = 0;
 #pragma unroll
       for (uint32_t u = 0; u < 2; ++u) {
-        if (lane == 0) ptx::counter_wait(ptx::smem_u32(&s_issued[wg]), 2u * lvl + u + 1u);  // issued: the parity is now exact
-        __syncwarp();
-        const uint32_t tk = *reinterpret_cast<volatile uint32_t*>(&s_tk[4 * wg + 2 * (lvl & 1) + u]), acc = tk % kAccs, use = tk / kAccs;
-        ptx::mbar_wait(ptx::smem_u32(&bar_mma_done[acc]), use & 1u);
+        ptx::mbar_wait(ptx::smem_u32(&bar_done[2 * wg + u]), lvl & 1u);
+        const uint32_t acc = *reinterpret_cast<volatile uint32_t*>(&s_tk[2 * wg + u]);
         ptx::tc_fence_after_sync();
         stamp(u == 0 ? 5 : 9);
         float m;
@@ -387,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
         if (u == 0) stamp(8);
         ptx::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) ptx::counter_add_release(ptx::smem_u32(&s_free[acc]), 1u);
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_free[acc]));
         if (m > best) {  // strict: the lower unit keeps exact ties
           best = m;
           col = c + static_cast<int>(u) * kUnitCols;
@@ -504,7 +389,7 @@ int launch_rq_fwd_tc_v11(const RqFwdArgs& a, bool rot, const void* images, const
   V11Params p{static_cast<const uint8_t*>(images), static_cast<const uint8_t*>(cb32), debug};
   const int smem = smem_bytes(a.n_levels);
   auto go = [&](auto kernel) -> int {
-    if (int st = prepare_kernel(kernel, kLaunchRegs, smem)) return st;
+    if (int st = prepare_kernel(kernel, kOwnerRegs > kLaunchRegs ? kLaunchRegs : 0, smem)) return st;  // (the check guards a setmaxnreg.inc)
     kernel<<<grid, kThreads, smem, stream>>>(a, p);
     HV_CUDA_CHECK(cudaGetLastError());
     return HV_OK;
