@@ -78,19 +78,22 @@ size_t rq_bwd_workspace_bytes(int64_t n, int d, int k, int n_levels);
 // 1 / (sqrt(v) + eps) and 1 / max(sqrt(v), floor) on the special-function unit: sqrt.approx (max relative error 2^-23) and
 // rcp.approx followed by one Newton step (the reciprocal is then correctly rounded up to the last bit of its argument).
 // 6 instructions instead of the ~16 + slow-path branches of an IEEE sqrt and division; three of these per row and level.
+// The .ftz forms drop the denormal pre-/post-scaling (4 more instructions per call) and give the same results here: the
+// reciprocals' arguments are >= 1e-8, and a denormal sum of squares (|v| < 1e-19) vanishes against the 1e-8 / 1e-6 it is
+// added to or clamped at.
 __device__ __forceinline__ float fast_rcp(float d) {
   float r;
-  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(d));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
   return fmaf(fmaf(-d, r, 1.0f), r, r);
 }
 __device__ __forceinline__ float fast_inv_norm_eps(float v, float eps) {
   float s;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(v));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(v));
   return fast_rcp(s + eps);
 }
 __device__ __forceinline__ float fast_inv_norm_floor(float v, float floor) {
   float s;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(v));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(v));
   return fast_rcp(fmaxf(s, floor));
 }
 

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mlp_kernel(EncArgs a) {
   uint64_t* h_ready = d_ready + 1;         // the 8 epilogue warps have packed / drained it (4 completions per tile)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(h_ready + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = ptx::warp_index();
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {

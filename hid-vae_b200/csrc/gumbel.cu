@@ -24,6 +24,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace hv {
 namespace {
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(kThreads) gumbel_fwd_kernel(GumbelArgs a) {
   float* s_red = s_cn + kMaxK + (threadIdx.x >> 5) * 32 * (D + 1);
   load_codebook<D>(a, s_cb, s_cn);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ptx::warp_index(), lane = threadIdx.x & 31;
   const int blocks_per_lane = (a.k + 127) / 128;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * kWarps + warp; row < a.n; row += static_cast<int64_t>(gridDim.x) * kWarps) {
     float x[D];
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kThreads) gumbel_bwd_kernel(GumbelArgs a) {
   float* s_red = s_ge + kTile * D + (threadIdx.x >> 5) * 32 * (D + 1);
   load_codebook<D>(a, s_cb, s_cn);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ptx::warp_index(), lane = threadIdx.x & 31;
   const int blocks_per_lane = (a.k + 127) / 128;
   const float inv_t = 1.0f / a.temperature;
   float acc[D];

@@ -13,6 +13,7 @@
 //                             (K * N index reads out of L2) and adds its members in a fixed-shape tree.
 //   hv_kmeans_finalize    means, empty-cluster reseed, max centroid shift: one warp per cluster.
 #include "common.cuh"
+#include "ptx.cuh"
 #include "sort.cuh"
 
 namespace hv {
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(kAccThreads) kmeans_accumulate_kernel(const fl
   __shared__ float s_part[kAccThreads / 32][D + 1];
   const int c = blockIdx.x;
   const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
+  const int lane = tid & 31, warp = ptx::warp_index();
 
   float acc[D];
 #pragma unroll
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) kmeans_segsum_kernel(const float* __restr
                                                             const uint32_t* __restrict__ rows, int k, float* __restrict__ sums,
                                                             float* __restrict__ counts) {
   constexpr int PER = (D + 31) / 32;
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int c = ptx::uniform((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= k) return;
   const int64_t lo = lower_bound_u64(keys, n, static_cast<uint64_t>(c));
@@ -169,7 +170,7 @@ int launch_segmented(const float* x, int64_t n, const int64_t* assign, const int
 __global__ void __launch_bounds__(256) kmeans_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ counts,
                                                              const float* __restrict__ reseed_rows, int k, int d,
                                                              float* __restrict__ centroids, float* __restrict__ stats) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int c = ptx::uniform((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= k) return;
   const float cnt = counts[c];

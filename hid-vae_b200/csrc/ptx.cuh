@@ -12,6 +12,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// The warp's index inside the CTA as a value the compiler KNOWS to be warp-uniform (a broadcast from lane 0).  With the plain
+// threadIdx.x >> 5, every branch or loop bound derived from the warp index counts as divergent, and each warp-collective
+// instruction below it (shfl.sync, vote, bar, tcgen05 .sync.aligned) gets a WARPSYNC.COLLECTIVE / ENDCOLLECTIVE pair, register
+// moves and sometimes a duplicated code path (the row loop of the backward kernel shrank from 1376 to 872 instructions).
+__device__ __forceinline__ int warp_index() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ int uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // One lane of the (converged) warp: ptxas knows that a region guarded by elect.sync has a single active thread, so
 // operands that must live in uniform registers (tcgen05.mma descriptors) need no per-value "waterfall" loop --
 // unlike a region guarded by `lane == 0`.

@@ -15,6 +15,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace hv {
 namespace {
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(kBwdThreads, NL > 0 ? HV_BWD_MINB : 1) rq_bwd_
   const int64_t lkd = static_cast<int64_t>(a.n_levels) * a.k * D;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
-  const int warp_global = (blockIdx.x * kBwdThreads + threadIdx.x) >> 5;
+  const int warp_global = ptx::uniform((blockIdx.x * kBwdThreads + threadIdx.x) >> 5);  // (see ptx::warp_index)
   const int n_warps = (gridDim.x * kBwdThreads) >> 5;
   const int64_t n_groups = (a.n + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
   constexpr bool rot = ROT && TRAIN;
@@ -216,7 +217,9 @@ __global__ void __launch_bounds__(kBwd2Threads, 2) rq_bwd_smem_kernel(RqBwdArgs 
   const int64_t lkd = static_cast<int64_t>(NL) * a.k * D;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
-  const int warp_global = (blockIdx.x * kBwd2Threads + threadIdx.x) >> 5;
+  // (the broadcast tells the compiler that the value -- and with it the trip count of the row loop -- is warp-uniform: without it
+  // every shuffle of the loop carries a WARPSYNC.COLLECTIVE / ENDCOLLECTIVE pair and register moves)
+  const int warp_global = ptx::uniform((blockIdx.x * kBwd2Threads + threadIdx.x) >> 5);
   const int n_warps = (gridDim.x * kBwd2Threads) >> 5;
   const int64_t n_groups = (a.n + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
   float* gc_base = a.n_replicas > 0 ? a.replicas + static_cast<int64_t>(blockIdx.x % a.n_replicas) * lkd : a.g_codebooks;

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
   uint32_t* s_tmem = s_tk + 2 * kWGs;
   uint32_t* s_ts = s_tmem + 1;                       // [192] timestamps of block 0, warpgroup 0 (instrumented builds)
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = ptx::warp_index();
   const int lane = threadIdx.x & 31;
   const int wg = warp >> 2;
   const int q = warp & 3;        // TMEM lane quarter of this warp

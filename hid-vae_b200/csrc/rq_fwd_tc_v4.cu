@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
   uint32_t* cnt_acc_empty = cnt_a_ready + kMaxWg;                              // [kMaxWg] warp arrivals: 4 per drained unit
   uint32_t* s_tmem = cnt_acc_empty + kMaxWg;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = ptx::warp_index();
   const int lane = threadIdx.x & 31;
 
   if (warp == R::kProducerWarp && lane == 0) {

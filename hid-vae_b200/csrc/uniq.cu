@@ -9,6 +9,7 @@
 // radix sort, sort.cuh), identical tuples then sit in one run in ascending row order, and a thread per sorted position
 // walks the rest of its run -- O(B + pairs) instead of O(B^2) (the loss itself is a sum over pairs of identical tuples).
 #include "common.cuh"
+#include "ptx.cuh"
 #include "sort.cuh"
 
 namespace hv {
@@ -67,7 +68,7 @@ __device__ __forceinline__ void tile_keys(const UniqArgs& a, int64_t row0, uint6
     s_keys[threadIdx.x] = r < a.rows ? row_key(a, r) : 0ull;
     return;
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = ptx::warp_index();
   for (int t = warp; t < kTile; t += kTile / 32) {
     const int64_t r = row0 + t;
     uint64_t h = 0ull;
@@ -86,7 +87,7 @@ template <typename T>
 __device__ __forceinline__ T block_sum(T v, T* scratch) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = ptx::warp_index();
   __syncthreads();
   if (lane == 0) scratch[warp] = v;
   __syncthreads();

@@ -70,8 +70,11 @@ def test_gumbel_philox_noise_is_the_recorded_draw(ops):
         emb, ids, loss = ops.gumbel_apply(x_d, cb_d, 0.2, 0.25, uniforms=uniforms, seed=1234)
         (emb.sum() * 0.5 + loss.mean()).backward()
         outs.append((emb.detach(), ids, loss.detach(), x_d.grad, cb_d.grad))
-    for a, b in zip(*outs[:2]):
-        assert torch.equal(a, b) if a.dtype == torch.int64 else torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+    for name, a, b in zip(("emb", "ids", "loss", "g_x", "g_codebook"), *outs[:2]):
+        if name == "g_codebook":    # folded with atomics: the order of the additions differs from launch to launch
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6 * float(b.abs().max()))
+        else:
+            assert torch.equal(a, b), name
     u = ops.gumbel_uniforms(n, k, 1234, "cuda")
     assert float(u.min()) >= 0.0 and float(u.max()) < 1.0
     assert abs(float(u.mean()) - 0.5) < 2e-3 and abs(float(u.var()) - 1.0 / 12.0) < 1e-3
