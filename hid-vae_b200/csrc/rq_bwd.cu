@@ -323,6 +323,178 @@ __global__ void __launch_bounds__(kBwd2Threads, 2) rq_bwd_smem_kernel(RqBwdArgs 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same kernel with EIGHT floats of a row per lane (D / 8 lanes per row, 8 rows per warp at D = 32).  The kernel above is
+// bound by issue slots (ncu: 70 % issue utilisation, 554 instructions per 4 rows), and about half of them are the per-row
+// scalars -- shuffle reductions, three reciprocal norms, the rotation coefficients -- that every lane of a row repeats.
+// With half as many lanes per row each of those warp instructions serves twice as many rows and a reduction is one shuffle
+// shorter.  Registers: the chosen code rows are read from shared memory a second time in the backward sweep instead of
+// being kept (2 LDS.128 per level), so the kernel still runs 2 CTAs x 256 threads per SM.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kBwd8Threads = 256;
+
+struct F8 {
+  float v[8];
+};
+// a lane's eight floats of a row are two 16-byte pieces HALF A ROW apart (dims [4 sub, 4 sub + 4) and D/2 + the same): the
+// lanes of a row then cover whole 32-byte sectors with each instruction
+template <int D>
+__device__ __forceinline__ F8 ldg8(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + D / 2));
+  return F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+template <int D>
+__device__ __forceinline__ F8 lds8(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + D / 2);
+  return F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ float dot8(const F8& a, const F8& b) {
+  float s0 = a.v[0] * b.v[0], s1 = a.v[1] * b.v[1];
+#pragma unroll
+  for (int i = 2; i < 8; i += 2) s0 = fmaf(a.v[i], b.v[i], s0), s1 = fmaf(a.v[i + 1], b.v[i + 1], s1);
+  return s0 + s1;
+}
+
+template <int D, bool ROT, bool TRAIN, int NL>
+__global__ void __launch_bounds__(kBwd8Threads, 2) rq_bwd_smem8_kernel(RqBwdArgs a) {
+  constexpr int LPR = D / 8;
+  constexpr int ROWS_PER_WARP = 32 / LPR;
+  constexpr bool rot = ROT && TRAIN;
+  extern __shared__ __align__(16) float s_cb[];  // [NL][K][D]
+  {
+    const int total4 = NL * a.k * (D / 4);
+    for (int i = threadIdx.x; i < total4; i += kBwd8Threads)
+      reinterpret_cast<float4*>(s_cb)[i] = __ldg(reinterpret_cast<const float4*>(a.codebooks) + i);
+  }
+  __syncthreads();
+
+  const int64_t lkd = static_cast<int64_t>(NL) * a.k * D;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int warp_global = ptx::uniform((blockIdx.x * kBwd8Threads + threadIdx.x) >> 5);  // (see ptx::warp_index)
+  const int n_warps = (gridDim.x * kBwd8Threads) >> 5;
+  const int64_t n_groups = (a.n + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
+  float* gc_base = a.n_replicas > 0 ? a.replicas + static_cast<int64_t>(blockIdx.x % a.n_replicas) * lkd : a.g_codebooks;
+
+  // the next iteration's inputs
+  F8 nx, nge[NL];
+  int nid[NL];
+  float ngl;
+  auto fetch = [&](int64_t g) {
+    const int64_t row = g * ROWS_PER_WARP + lane / LPR;
+    const int64_t rrow = row < a.n ? row : 0;  // keep every lane in the shuffles; the stores are masked
+    nx = ldg8<D>(a.x + rrow * D + sub * 4);
+    ngl = a.g_loss != nullptr ? __ldg(a.g_loss + rrow * a.g_loss_stride) : 0.f;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      int64_t code = __ldg(a.ids + rrow * a.ids_row_stride + l * a.ids_level_stride);
+      code = code < 0 ? 0 : (code >= a.k ? a.k - 1 : code);
+      nid[l] = static_cast<int>(code);
+      if (a.g_emb != nullptr) {
+        nge[l] = ldg8<D>(a.g_emb + l * a.g_emb_level_stride + rrow * a.g_emb_row_stride + sub * 4);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nge[l].v[i] = 0.f;
+      }
+    }
+  };
+  if (warp_global < n_groups) fetch(warp_global);
+
+  for (int64_t g = warp_global; g < n_groups; g += n_warps) {
+    const int64_t row = g * ROWS_PER_WARP + lane / LPR;
+    const bool valid = row < a.n;
+    F8 r = nx;
+    const float gl = ngl;
+    F8 GE[NL];
+    const float* code_row[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) GE[l] = nge[l], code_row[l] = s_cb + (static_cast<int64_t>(l) * a.k + nid[l]) * D + sub * 4;
+    int id[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) id[l] = nid[l];
+    if (g + n_warps < n_groups) fetch(g + n_warps);
+
+    F8 R[NL];
+    float inv_r[NL], inv_e[NL], inv_s[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const F8 e = lds8<D>(code_row[l]);
+      R[l] = r;
+      if (rot) {  // (same expressions as rq_bwd_kernel)
+        const float rr = group_sum<LPR>(dot8(r, r));
+        const float ee = group_sum<LPR>(dot8(e, e));
+        const float re = group_sum<LPR>(dot8(r, e));
+        const float ir = fast_inv_norm_eps(rr, 1e-8f);
+        const float ie = fast_inv_norm_eps(ee, 1e-8f);
+        const float ru = rr * ir;
+        const float rq = re * ie;
+        const float ss = fmaf(2.0f * rq, ir, fmaf(ru, ir, ee * ie * ie));  // |u + q|^2 from the three row sums
+        const float rs = ru + rq;
+        const float is = fast_inv_norm_floor(ss, 1e-6f);
+        inv_r[l] = ir, inv_e[l] = ie, inv_s[l] = is;
+        const float a2 = 2.0f * rs * is * is, b2 = 2.0f * ru;
+        const float cr = 1.0f - a2 * ir, ce = (b2 - a2) * ie;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] -= fmaf(cr, r.v[i], ce * e.v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] -= e.v[i];
+      }
+    }
+
+    F8 G;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) G.v[i] = 0.f;
+    const float c2 = 2.0f * gl, cb2 = a.beta * c2;
+#pragma unroll
+    for (int l = NL - 1; l >= 0; --l) {
+      const F8 el = lds8<D>(code_row[l]);
+      const F8& rl = R[l];
+      F8 h, diff, ge_code;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h.v[i] = GE[l].v[i] - G.v[i];
+        diff.v[i] = rl.v[i] - el.v[i];
+        ge_code.v[i] = -c2 * diff.v[i];
+      }
+      if (TRAIN) {
+        if (rot) {
+          const float ir = inv_r[l], ie = inv_e[l], is = inv_s[l];
+          F8 u, q, w;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            u.v[i] = rl.v[i] * ir;
+            q.v[i] = el.v[i] * ie;
+            w.v[i] = (u.v[i] + q.v[i]) * is;
+          }
+          const float hw2 = 2.0f * group_sum<LPR>(dot8(h, w));
+          const float hq2 = 2.0f * group_sum<LPR>(dot8(h, q));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h.v[i] = h.v[i] - hw2 * w.v[i] + hq2 * u.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) G.v[i] += h.v[i] + cb2 * diff.v[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          G.v[i] += cb2 * diff.v[i];
+          ge_code.v[i] += h.v[i];
+        }
+      }
+      if (valid) {
+        float* gc = gc_base + (static_cast<int64_t>(l) * a.k + id[l]) * D + sub * 4;
+        red_add_v4(gc, make_float4(ge_code.v[0], ge_code.v[1], ge_code.v[2], ge_code.v[3]));
+        red_add_v4(gc + D / 2, make_float4(ge_code.v[4], ge_code.v[5], ge_code.v[6], ge_code.v[7]));
+      }
+    }
+    if (valid) {
+      float* gx = a.g_x + row * D + sub * 4;
+      *reinterpret_cast<float4*>(gx) = make_float4(G.v[0], G.v[1], G.v[2], G.v[3]);
+      *reinterpret_cast<float4*>(gx + D / 2) = make_float4(G.v[4], G.v[5], G.v[6], G.v[7]);
+    }
+  }
+}
+
 // shapes the shared-memory variant serves: exact-level instantiation, codebooks within 96 KB, no per-level loss gradient,
 // and enough rows for 2 persistent CTAs per SM to amortise staging the codebooks
 template <int D>
@@ -355,10 +527,19 @@ int launch_d(const RqBwdArgs& a, bool rot, cudaStream_t stream) {
     HV_CUDA_CHECK(cudaGetLastError());
     return HV_OK;
   };
+  auto go8 = [&](auto kernel) -> int {
+    if (int st = prepare_kernel(kernel, 0, smem_bytes)) return st;
+    kernel<<<2 * props.sm_count, kBwd8Threads, smem_bytes, stream>>>(a);
+    HV_CUDA_CHECK(cudaGetLastError());
+    return HV_OK;
+  };
   auto pick = [&](auto nl) -> int {
     constexpr int NLc = decltype(nl)::value;
     if constexpr (NLc > 0 && (D == 16 || D == 32 || D == 64)) {
       if (smem_variant) {
+#ifndef HV_BWD_NO_LPR8
+        if (r) return go8(rq_bwd_smem8_kernel<D, true, true, NLc>);  // the rotation-trick chain is the instruction-bound one
+#endif
         if (r) return go2(rq_bwd_smem_kernel<D, true, true, NLc>);
         return train ? go2(rq_bwd_smem_kernel<D, false, true, NLc>) : go2(rq_bwd_smem_kernel<D, false, false, NLc>);
       }

@@ -271,8 +271,10 @@ def test_backward_vs_oracle_autograd(ops, algo, mname, training, shape):
                          ids=lambda s: "n%d_d%d_k%d_L%d" % s)
 def test_backward_large_n_variant_equals_row_kernel(ops, mname, training, shape):
     """From 65,536 rows on (codebooks within 96 KB) the backward runs its shared-memory / prefetching variant
-    (rq_bwd_smem_kernel).  The same rows in two calls below that size run the row kernel, which the oracle tests above
-    pin: g_x must be bit-identical (same expressions per row), the codebook gradient equal up to the order of the sums."""
+    (rq_bwd_smem_kernel; rq_bwd_smem8_kernel for the rotation trick).  The same rows in two calls below that size run the
+    row kernel, which the oracle tests above pin: g_x must be bit-identical where the per-row expressions are the same, and
+    equal up to the order of the row sums (eight floats per lane instead of four) for the rotation-trick kernel -- with the
+    bar of the oracle comparison; the codebook gradient equal up to the order of the sums."""
     n, d, k, L = shape
     beta = 0.4
     x = _dev(unit_rows(n, d, seed=51))
@@ -286,9 +288,36 @@ def test_backward_large_n_variant_equals_row_kernel(ops, mname, training, shape)
     h = n // 2
     gx_a, gcb_a = ops.rq_backward(x[:h], cbs, ids[:h], mode, bool(training), beta, g_emb[:, :h].contiguous(), g_loss[:h], None)
     gx_b, gcb_b = ops.rq_backward(x[h:], cbs, ids[h:], mode, bool(training), beta, g_emb[:, h:].contiguous(), g_loss[h:], None)
-    assert torch.equal(gx, torch.cat([gx_a, gx_b]))
+    gx_rows = torch.cat([gx_a, gx_b])
+    if mname == "rot" and training:
+        torch.testing.assert_close(gx, gx_rows, rtol=2e-5, atol=1e-6 * max(1.0, float(gx_rows.abs().max())))
+    else:
+        assert torch.equal(gx, gx_rows)
     ref = gcb_a + gcb_b
     torch.testing.assert_close(gcb, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("mname", ["ste", "rot"])
+@pytest.mark.parametrize("shape", [(65536 + 77, 32, 256, 3), (66001, 64, 128, 2)], ids=lambda s: "n%d_d%d_k%d_L%d" % s)
+def test_backward_large_n_variant_vs_oracle_autograd(ops, mname, shape):
+    """The shared-memory backward kernels (from 65,536 rows on) against the oracle's autograd directly, on the oracle's own
+    ids (so that no near-tie row can follow another code)."""
+    n, d, k, L = shape
+    beta = 0.4
+    x = unit_rows(n, d, seed=61)
+    cbs = make_codebooks(L, k, d, seed=62)
+    gen = torch.Generator().manual_seed(63)
+    g_emb = torch.randn(n, d, L, generator=gen)
+    g_loss = torch.randn(n, generator=gen)
+    x_o = x.clone().requires_grad_(True)
+    cb_o = [cbs[l].clone().requires_grad_(True) for l in range(L)]
+    ref = O.rq_forward(x_o, cb_o, MODES[mname], beta, True)
+    ((ref.embeddings * g_emb).sum() + (ref.quantize_loss * g_loss).sum()).backward()
+    gx, gcb = ops.rq_backward(_dev(x), _dev(cbs), _dev(ref.sem_ids), MODES[mname], True, beta,
+                              _dev(g_emb.permute(2, 0, 1).contiguous()), _dev(g_loss), None)
+    torch.testing.assert_close(gx.cpu(), x_o.grad, rtol=2e-5, atol=1e-6 * max(1.0, float(x_o.grad.abs().max())))
+    for l in range(L):   # sums of ~n / k terms per code: the bar scales with the gradient
+        torch.testing.assert_close(gcb.cpu()[l], cb_o[l].grad, rtol=1e-4, atol=1e-5 * max(1.0, float(cb_o[l].grad.abs().max())))
 
 
 def test_backward_broadcast_grad(ops):
