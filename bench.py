@@ -161,6 +161,39 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def bind_host_memory_near(local_rank):
+    """Best effort, before the pinned buffers of the end-to-end leg are allocated: run this process on the CPUs of the NUMA node
+    the GPU hangs off and prefer that node's memory (set_mempolicy), so that eight ranks do not pull their 3 GB of pinned items
+    through one socket's memory controllers and the inter-socket link.  A no-op on single-node hosts (the 1-GPU boxes are 16-vCPU
+    single-node VMs).  Returns what it found and did, for the JSON line."""
+    info = dict(gpu_numa_node=None, nodes=None, bound=False)
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        info["nodes"] = len(nodes)
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0 or len(nodes) < 2:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238              # x86_64
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))
+        info["bound"] = bool(cpus) and rc == 0
+    except Exception as exc:                                     # never fail the bench over placement
+        info["error"] = repr(exc)[:120]
+    return info
+
+
 def time_steps(fn, steps, warmup, flush=None):
     """W warm-ups, then K steps each bracketed by CUDA events on the current stream (optionally an L2 flush between
     steps); returns the per-step milliseconds."""
@@ -250,9 +283,15 @@ def run_native(args):
 
     # ---- e2e: the same call on PINNED HOST items: chunk H2D + kernels + D2H of the id table inside the timed region ----
     n_e = min(E2E_ITEMS, n)
+    cpus_before = os.sched_getaffinity(0)
+    host_numa = bind_host_memory_near(local)
     x_host = torch.empty((n_e, DIMS[0]), dtype=torch.float32).pin_memory()
     x_host.copy_(x[:n_e])
     ids_host = torch.empty((n_e, N_LEVELS), dtype=torch.int64).pin_memory()
+    if host_numa["bound"]:                                   # the pages are placed: give the CPU legs every core back
+        import ctypes
+        os.sched_setaffinity(0, cpus_before)
+        ctypes.CDLL(None).syscall(238, 0, None, 0)           # set_mempolicy(MPOL_DEFAULT)
 
     def e2e_step():
         ids_host.copy_(tok.precompute_corpus_ids(x_host), non_blocking=True)
@@ -333,7 +372,7 @@ def run_native(args):
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=n_e * DIMS[0] * 4, d2h_bytes_per_step=n_e * N_LEVELS * 8,
                              ms_per_step=e2e_total / args.steps, items_per_step_per_gpu=n_e,
                              call="HSemanticIdTokenizer.precompute_corpus_ids(pinned host tensor) + id table -> pinned host",
-                             ids_equal_device_resident_pass=e2e_same,
+                             ids_equal_device_resident_pass=e2e_same, host_numa=host_numa,
                              pcie_gbs=(n_e * (DIMS[0] * 4 + N_LEVELS * 8)) / (e2e_total / args.steps * 1e-3) / 1e9),
                     gpu_launches=(2 * n_chunks + 1) * args.steps, roofline=roofline, cpu_baseline=cpu, clocks=clocks, impl="native")
         if sweep is not None:
