@@ -308,6 +308,34 @@ def run_native(args):
     torch.cuda.synchronize()
     e2e_same = bool(torch.equal(ids_dev.cpu(), ids_host))      # host-fed and device-resident passes agree bit for bit
 
+    # ---- the same workload on a catalogue kept in HALF precision (a data format beside the path: half the HBM / PCIe bytes;
+    #      the fused encoder rounds fp32 items to fp16 anyway, so the id table must equal the fp32 catalogue's bit for bit).
+    #      Reported beside the headline, never instead of it: the reference's items are fp32. ----
+    half_cat = None
+    if not args.no_sweep:
+        x16 = x.half()
+        step16 = lambda: tok.precompute_corpus_ids(x16)
+        ms16 = time_steps(step16, args.steps, args.warmup)
+        ids16 = tok.precompute_corpus_ids(x16[:n_e]).clone()
+        x16_host = torch.empty((n_e, DIMS[0]), dtype=torch.float16).pin_memory()
+        x16_host.copy_(x16[:n_e])
+
+        def e2e16_step():
+            ids_host.copy_(tok.precompute_corpus_ids(x16_host), non_blocking=True)
+
+        if world > 1:
+            dist.barrier()
+        e16 = time_steps(e2e16_step, args.steps, args.warmup)
+        t16 = torch.tensor([sum(ms16), sum(e16)], device=dev)
+        if world > 1:
+            dist.all_reduce(t16, op=dist.ReduceOp.MAX)
+        half_cat = dict(items="fp16 [N, 768] (x.half() of the same synthetic catalogue)",
+                        value=world * n * args.steps / (float(t16[0]) * 1e-3), unit=UNIT, ms_per_step=float(t16[0]) / args.steps,
+                        e2e=dict(value=world * n_e * args.steps / (float(t16[1]) * 1e-3), unit=UNIT, ms_per_step=float(t16[1]) / args.steps,
+                                 h2d_bytes_per_step=n_e * DIMS[0] * 2, d2h_bytes_per_step=n_e * N_LEVELS * 8),
+                        ids_equal_fp32_catalogue=bool(torch.equal(ids16, ids_dev)))
+        del x16, x16_host
+
     # ---- per-kernel durations at the step's launch shape (CUDA events around each C-ABI call) -> roofline ----
     model = tok.hrq_vae
     image = model.encoder._weight_image()
@@ -375,6 +403,8 @@ def run_native(args):
                              ids_equal_device_resident_pass=e2e_same, host_numa=host_numa,
                              pcie_gbs=(n_e * (DIMS[0] * 4 + N_LEVELS * 8)) / (e2e_total / args.steps * 1e-3) / 1e9),
                     gpu_launches=(2 * n_chunks + 1) * args.steps, roofline=roofline, cpu_baseline=cpu, clocks=clocks, impl="native")
+        if half_cat is not None:
+            line["half_precision_catalogue"] = half_cat
         if sweep is not None:
             line["sweep"] = sweep
         if train_dp is not None:

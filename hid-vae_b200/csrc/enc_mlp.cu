@@ -27,6 +27,8 @@
 // converted while layer 2 runs, and the weight ring runs ahead across tiles.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -105,14 +107,17 @@ __device__ __forceinline__ void epilogue_pack(uint32_t src, uint32_t dst) {
 }
 
 struct EncArgs {
-  const float* x;
+  const void* x;           // [N, 768] fp32, or fp16 for the HALF_IN instantiation
   const uint8_t* image;
   float* z;
   int64_t n;
   int normalize;
 };
 
-template <bool PRECISE>
+// HALF_IN: the items are already fp16 (a catalogue kept in half precision: half the HBM / PCIe bytes).  The fp32 path
+// rounds x to fp16 (round to nearest even) before the first GEMM, so fp16 items that are the rounded fp32 items give
+// bit-identical z; the converter warps then only move 16-byte pieces into the operand layout.
+template <bool PRECISE, bool HALF_IN>
 __global__ void __launch_bounds__(kThreads, 1) enc_mlp_kernel(EncArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
@@ -164,8 +169,9 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mlp_kernel(EncArgs a) {
         if (i + 1 < my_tiles) {
           const int64_t r0 = tile_row0(i + 1);
           const int64_t rows = a.n - r0 < kTileRows ? a.n - r0 : kTileRows;
-          const uint8_t* p = reinterpret_cast<const uint8_t*>(a.x + r0 * kIn);
-          const int64_t bytes = rows * kIn * 4;
+          constexpr int kElem = HALF_IN ? 2 : 4;
+          const uint8_t* p = static_cast<const uint8_t*>(a.x) + r0 * kIn * kElem;
+          const int64_t bytes = rows * kIn * kElem;
           for (int64_t off = 0; off < bytes; off += 32768)
             ptx::bulk_prefetch_l2(p + off, static_cast<uint32_t>(bytes - off < 32768 ? bytes - off : 32768));
         }
@@ -288,33 +294,62 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mlp_kernel(EncArgs a) {
     // two fully coalesced 256-byte row segments -- and stores 4 fp16 (8 bytes) at K group (piece >> 1), row, half
     // (piece & 1).  With the K-group stride padded to 2064 bytes the 16 lanes of a row cover 128 consecutive bytes of
     // bank space: conflict free.
-    auto load_chunk = [&](int i, int c, float4 (&v)[8]) {
-      const int64_t r0 = tile_row0(i) + 16 * we + (lane >> 4);
-      const float* p = a.x + r0 * kIn + c * 64 + (lane & 15) * 4;
+    // (fp32 items) 8 x 16-byte loads of 4 floats per lane and chunk; (fp16 items) instruction k of a warp reads rows
+    // 16 we + 4 k + (lane >> 3), 16-byte piece lane & 7 = one whole K group of 8 fp16: four 128-byte row segments per
+    // instruction, stored as they are.
+    constexpr int kLoads = HALF_IN ? 4 : 8;
+    using Piece = typename std::conditional<HALF_IN, uint4, float4>::type;
+    auto load_chunk = [&](int i, int c, Piece (&v)[kLoads]) {
+      if constexpr (HALF_IN) {
+        const int64_t r0 = tile_row0(i) + 16 * we + (lane >> 3);
+        const __half* p = static_cast<const __half*>(a.x) + r0 * kIn + c * 64 + (lane & 7) * 8;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (r0 + 2 * k < a.n) {
-          v[k] = ldg_stream(p + static_cast<int64_t>(2 * k) * kIn);
-        } else {
-          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 4; ++k) {
+          if (r0 + 4 * k < a.n) {
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w)
+                         : "l"(p + static_cast<int64_t>(4 * k) * kIn));
+          } else {
+            v[k] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      } else {
+        const int64_t r0 = tile_row0(i) + 16 * we + (lane >> 4);
+        const float* p = static_cast<const float*>(a.x) + r0 * kIn + c * 64 + (lane & 15) * 4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (r0 + 2 * k < a.n) {
+            v[k] = ldg_stream(p + static_cast<int64_t>(2 * k) * kIn);
+          } else {
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
     };
-    auto store_chunk = [&](const float4 (&v)[8]) {
+    auto store_chunk = [&](const Piece (&v)[kLoads]) {
       const uint32_t s = aseq % kAStages, use = aseq / kAStages;
       if (use > 0) ptx::mbar_wait(ptx::smem_u32(&a_empty[s]), (use - 1) & 1u);
-      const uint32_t base = ptx::smem_u32(s_a + s * kAStageBytes) + ((lane & 15) >> 1) * kALbo + (16 * we + (lane >> 4)) * 16 + (lane & 1) * 8;
+      if constexpr (HALF_IN) {
+        const uint32_t base = ptx::smem_u32(s_a + s * kAStageBytes) + (lane & 7) * kALbo + (16 * we + (lane >> 3)) * 16;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t lo = pack_f16(v[k].x, v[k].y), hi = pack_f16(v[k].z, v[k].w);
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + 2 * k * 16), "r"(lo), "r"(hi) : "memory");
+        for (int k = 0; k < 4; ++k)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + 4 * k * 16), "r"(v[k].x), "r"(v[k].y), "r"(v[k].z),
+                       "r"(v[k].w)
+                       : "memory");
+      } else {
+        const uint32_t base = ptx::smem_u32(s_a + s * kAStageBytes) + ((lane & 15) >> 1) * kALbo + (16 * we + (lane >> 4)) * 16 + (lane & 1) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t lo = pack_f16(v[k].x, v[k].y), hi = pack_f16(v[k].z, v[k].w);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + 2 * k * 16), "r"(lo), "r"(hi) : "memory");
+        }
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(ptx::smem_u32(&a_full[s]));
       ++aseq;
     };
     auto convert = [&](int i, int c0, int c1) {  // chunks [c0, c1) of tile i (an even count), loads one chunk ahead of the stores
-      float4 va[8], vb[8];
+      Piece va[kLoads], vb[kLoads];
       load_chunk(i, c0, va);
 #pragma unroll 1
       for (int c = c0; c < c1; c += 2) {
@@ -499,34 +534,34 @@ int hv_encoder_pack_weights(const float* const* weights, int n_layers, const int
   return HV_OK;
 }
 
-int hv_encoder_forward(const float* x, int64_t n, int n_layers, const int* dims, const void* workspace, size_t workspace_bytes,
-                       int normalize, int precise_silu, float* z, void* stream) {
+static int encoder_forward_impl(const char* who, const void* x, bool half_in, int64_t n, int n_layers, const int* dims,
+                                const void* workspace, size_t workspace_bytes, int normalize, int precise_silu, float* z, void* stream) {
   using namespace hv;
   if (n < 0) {
-    set_error("hv_encoder_forward: bad row count %lld", static_cast<long long>(n));
+    set_error("%s: bad row count %lld", who, static_cast<long long>(n));
     return HV_ERR_BAD_SHAPE;
   }
   if (!shape_ok(n_layers, dims)) {
-    set_error("hv_encoder_forward: no fused instantiation for this MLP shape (served: 768-512-256-128-32)");
+    set_error("%s: no fused instantiation for this MLP shape (served: 768-512-256-128-32)", who);
     return HV_ERR_UNSUPPORTED;
   }
   if (n == 0) return HV_OK;
   if (!x || !workspace || !z) {
-    set_error("hv_encoder_forward: null pointer");
+    set_error("%s: null pointer", who);
     return HV_ERR_NULL;
   }
   if (!aligned16(x) || !aligned16(z) || !aligned16(workspace)) {
-    set_error("hv_encoder_forward: x, z and the weight image must be 16-byte aligned");
+    set_error("%s: x, z and the weight image must be 16-byte aligned", who);
     return HV_ERR_MISALIGNED;
   }
   if (workspace_bytes < kImageBytes) {
-    set_error("hv_encoder_forward: the weight image is %zu bytes (got %zu)", kImageBytes, workspace_bytes);
+    set_error("%s: the weight image is %zu bytes (got %zu)", who, kImageBytes, workspace_bytes);
     return HV_ERR_WORKSPACE;
   }
   DeviceProps props;
   if (int st = device_props(&props)) return st;
   if (props.cc_major != 10) {
-    set_error("hv_encoder_forward: built for sm_100a, current device is sm_%d%d", props.cc_major, props.cc_minor);
+    set_error("%s: built for sm_100a, current device is sm_%d%d", who, props.cc_major, props.cc_minor);
     return HV_ERR_UNSUPPORTED;
   }
   const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
@@ -538,7 +573,20 @@ int hv_encoder_forward(const float* x, int64_t n, int n_layers, const int* dims,
     HV_CUDA_CHECK(cudaGetLastError());
     return HV_OK;
   };
-  return precise_silu ? go(enc_mlp_kernel<true>) : go(enc_mlp_kernel<false>);
+  if (half_in) return precise_silu ? go(enc_mlp_kernel<true, true>) : go(enc_mlp_kernel<false, true>);
+  return precise_silu ? go(enc_mlp_kernel<true, false>) : go(enc_mlp_kernel<false, false>);
+}
+
+int hv_encoder_forward(const float* x, int64_t n, int n_layers, const int* dims, const void* workspace, size_t workspace_bytes,
+                       int normalize, int precise_silu, float* z, void* stream) {
+  return encoder_forward_impl("hv_encoder_forward", x, false, n, n_layers, dims, workspace, workspace_bytes, normalize, precise_silu, z,
+                              stream);
+}
+
+int hv_encoder_forward_f16(const void* x_f16, int64_t n, int n_layers, const int* dims, const void* workspace, size_t workspace_bytes,
+                           int normalize, int precise_silu, float* z, void* stream) {
+  return encoder_forward_impl("hv_encoder_forward_f16", x_f16, true, n, n_layers, dims, workspace, workspace_bytes, normalize,
+                              precise_silu, z, stream);
 }
 
 }  // extern "C"

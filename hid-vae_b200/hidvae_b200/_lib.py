@@ -59,6 +59,8 @@ SIGNATURES = {
     "hv_encoder_pack_weights": (c_int, [POINTER(c_void_p), c_int, POINTER(c_int), c_void_p, c_size_t, c_void_p]),
     "hv_encoder_forward": (c_int, [c_void_p, c_int64, c_int, POINTER(c_int), c_void_p, c_size_t, c_int, c_int, c_void_p,
                                    c_void_p]),
+    "hv_encoder_forward_f16": (c_int, [c_void_p, c_int64, c_int, POINTER(c_int), c_void_p, c_size_t, c_int, c_int, c_void_p,
+                                       c_void_p]),
     "hv_peer_allreduce_chunks": (c_int, [c_int64]),
     "hv_peer_allreduce_set_timeout_ms": (None, [c_int64]),
     "hv_peer_allreduce_status": (c_int, [ctypes.c_uint32, POINTER(c_int), POINTER(c_int)]),

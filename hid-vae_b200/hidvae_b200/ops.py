@@ -309,10 +309,13 @@ def encoder_pack(weights) -> EncoderImage:
 
 def encoder_forward(x: Tensor, image: EncoderImage, normalize: bool = False, precise_silu: bool = False,
                     out: Optional[Tensor] = None) -> Tensor:
-    """z [N, out] = the MLP applied to x [N, in] fp32 (hv_encoder_forward): one fused tcgen05 kernel."""
+    """z [N, out] = the MLP applied to x [N, in] (hv_encoder_forward / hv_encoder_forward_f16): one fused tcgen05 kernel.
+    x is fp32, or fp16 -- a catalogue kept in half precision moves half the bytes; the kernel rounds fp32 items to fp16 before
+    the first GEMM anyway, so `x.half()` gives bit-identical z."""
     image, dims = image.data, image.dims
     _require_cuda(x, image)
-    x = _f32c(x)
+    half_in = x.dtype == torch.float16
+    x = x.contiguous() if half_in else _f32c(x)
     if x.dim() != 2 or x.shape[1] != dims[0]:
         raise ValueError(f"encoder_forward: x {tuple(x.shape)} does not match the encoder input width {dims[0]}")
     n = x.shape[0]
@@ -320,8 +323,9 @@ def encoder_forward(x: Tensor, image: EncoderImage, normalize: bool = False, pre
     if z.shape != (n, dims[-1]) or z.dtype != torch.float32 or not z.is_contiguous():
         raise ValueError("encoder_forward: out must be contiguous fp32 [N, out]")
     with torch.cuda.device(x.device):
-        check(lib.hv_encoder_forward(x.data_ptr(), n, len(dims) - 1, _dims_array(dims), image.data_ptr(), image.numel(),
-                                     int(bool(normalize)), int(bool(precise_silu)), z.data_ptr(), _stream(x)))
+        fn = lib.hv_encoder_forward_f16 if half_in else lib.hv_encoder_forward
+        check(fn(x.data_ptr(), n, len(dims) - 1, _dims_array(dims), image.data_ptr(), image.numel(),
+                 int(bool(normalize)), int(bool(precise_silu)), z.data_ptr(), _stream(x)))
     return z
 
 

@@ -55,8 +55,8 @@ class MLP(nn.Module):
         return [m.weight for m in self.mlp if isinstance(m, nn.Linear)]
 
     def fused_available(self, x: Tensor) -> bool:
-        """The fused kernel serves this call: CUDA fp32 rows, no autograd, no active dropout, widths instantiated."""
-        if not x.is_cuda or x.dtype != torch.float32 or x.dim() < 2 or torch.is_grad_enabled():
+        """The fused kernel serves this call: CUDA fp32 (or fp16) rows, no autograd, no active dropout, widths instantiated."""
+        if not x.is_cuda or x.dtype not in (torch.float32, torch.float16) or x.dim() < 2 or torch.is_grad_enabled():
             return False
         if self.training and self.dropout != 0:
             return False
@@ -81,6 +81,7 @@ class MLP(nn.Module):
             z = ops.encoder_forward(x.reshape(-1, self.input_dim), self._weight_image(), normalize=self.normalize,
                                     precise_silu=self.precise_silu)
             return z.reshape(*x.shape[:-1], self.out_dim)
+        x = x.float()   # (fp16 items are served by the fused kernel only; every other path computes from fp32)
         if x.is_cuda and not torch.is_grad_enabled() and self.inference_precision != "fused":
             with _matmul_tf32(self.inference_precision == "tf32"):
                 return self.mlp(x)

@@ -202,6 +202,9 @@ class HRqVae(nn.Module, _HubMixin):
         return next(self.encoder.parameters()).device
 
     def encode(self, x: Tensor) -> Tensor:
+        # fp16 items (a catalogue stored in half precision) go to the fused encoder as they are; everything else is fp32
+        if x.dtype == torch.float16 and getattr(self.encoder, "inference_precision", None) == "fused" and self.encoder.fused_available(x):
+            return self.encoder(x)
         return self.encoder(x.float())
 
     def decode(self, x: Tensor) -> Tensor:

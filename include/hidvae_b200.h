@@ -207,6 +207,14 @@ int hv_encoder_pack_weights(const float* const* weights, int n_layers, const int
                             void* stream);
 int hv_encoder_forward(const float* x, int64_t n, int n_layers, const int* dims, const void* workspace, size_t workspace_bytes,
                        int normalize, int precise_silu, float* z, void* stream);
+/*
+ * The same pass for items stored in half precision: x_f16 [N, dims[0]] fp16 row-major (a catalogue kept as fp16 moves half
+ * the bytes over PCIe and out of HBM; the reference keeps its item embeddings as a float tensor it slices per batch,
+ * modules/tokenizer/h_semids.py:120-127).  hv_encoder_forward rounds fp32 items to fp16 (round to nearest even) before the
+ * first GEMM, so items that are the rounded fp32 items give bit-identical z.
+ */
+int hv_encoder_forward_f16(const void* x_f16, int64_t n, int n_layers, const int* dims, const void* workspace, size_t workspace_bytes,
+                           int normalize, int precise_silu, float* z, void* stream);
 
 /*
  * Data-parallel exchange of a small fp32 buffer (the codebook gradient, train_hidvae.py's DDP all-reduce) as ONE kernel

@@ -157,3 +157,46 @@ def test_module_uses_fused_kernel_only_for_inference(weights):
         y_neg_ref = mlp(x)
         assert float((y_neg - y_neg_ref).abs().max()) <= TOL
         assert float((y_neg - y).abs().max()) > 0.05
+
+
+@pytest.mark.parametrize("n", [1, 129, 5000, 148 * 128 + 77])
+@pytest.mark.parametrize("normalize", [0, 1])
+def test_half_precision_items_are_bit_identical_to_rounded_fp32_items(ops, weights, n, normalize):
+    """hv_encoder_forward_f16: items stored as fp16.  The fp32 kernel rounds its items to fp16 (round to nearest even) before
+    the first GEMM, so feeding x.half() must give the SAME z bit for bit -- and, like the fp32 call, stay within the TF32-grade
+    bar of the fp32 oracle on the original items."""
+    x = _x(n, 700 + n)
+    image = ops.encoder_pack([w.cuda() for w in weights])
+    z32 = ops.encoder_forward(x.cuda(), image, normalize=bool(normalize))
+    z16 = ops.encoder_forward(x.cuda().half(), image, normalize=bool(normalize))
+    assert z16.dtype == torch.float32 and torch.equal(z16, z32)
+    z16r = ops.encoder_forward(x.half().float().cuda(), image, normalize=bool(normalize))   # the rounded items as fp32
+    assert torch.equal(z16r, z32)
+    ref = OE.mlp_forward(x, weights, bool(normalize))
+    bar = TOL if normalize else TOL * float(ref.abs().max())
+    assert float((z16.cpu() - ref).abs().max()) <= bar
+
+
+def test_half_precision_catalogue_through_the_tokenizer(ops, weights):
+    """precompute_corpus_ids on an fp16 catalogue (device tensor and pinned host tensor): the id table equals the fp32
+    catalogue's bit for bit with the fused encoder; with encoder_precision='fp32' the items are widened and the PyTorch
+    layers run (ids of the rounded items)."""
+    from modules.tokenizer.h_semids import HSemanticIdTokenizer
+    n = 20000
+    x = _x(n, 12)
+    cbs = make_codebooks(3, 256, 32, seed=4)
+    tok = HSemanticIdTokenizer(input_dim=768, output_dim=32, hidden_dims=[512, 256, 128], codebook_size=256, n_layers=3,
+                               n_cat_feats=0, hrqvae_codebook_normalize=True, chunk_items=1 << 13, encoder_precision="fused").cuda()
+    with torch.no_grad():
+        for lin, w in zip([m for m in tok.hrq_vae.encoder.mlp if isinstance(m, torch.nn.Linear)], weights):
+            lin.weight.copy_(w)
+        for l, layer in enumerate(tok.hrq_vae.layers):
+            layer.embedding.weight.copy_(cbs[l])
+    ids32 = tok.precompute_corpus_ids(x.cuda()).clone()
+    ids16 = tok.precompute_corpus_ids(x.cuda().half()).clone()
+    assert torch.equal(ids16, ids32)
+    ids16_host = tok.precompute_corpus_ids(x.half().pin_memory()).clone()
+    assert torch.equal(ids16_host, ids32)
+    tok.hrq_vae.encoder.inference_precision = "fp32"
+    ids_fp32_path = tok.precompute_corpus_ids(x.cuda().half())
+    assert float((ids_fp32_path == ids32).all(dim=1).float().mean()) >= 0.99

@@ -38,6 +38,10 @@ if "encoder" in args.what:
     z = torch.empty(n, 32, device="cuda")
     t = ms(lambda: ops.encoder_forward(x, image, normalize=True, out=z), None)     # 3.2 GB of input: nothing survives in L2
     res["encoder_1Mi"] = dict(ms=t, tflops=bench.FLOP_ENCODER * n / t / 1e9, gitems=n / t / 1e6)
+    x16 = x.half()
+    t16 = ms(lambda: ops.encoder_forward(x16, image, normalize=True, out=z), None)
+    res["encoder_1Mi_fp16_items"] = dict(ms=t16, tflops=bench.FLOP_ENCODER * n / t16 / 1e9, gitems=n / t16 / 1e6)
+    del x16
     for small in (128, 4096, 12101):
         xs = x[:small]
         res[f"encoder_{small}"] = dict(ms=ms(lambda: ops.encoder_forward(xs, image, normalize=True)))
