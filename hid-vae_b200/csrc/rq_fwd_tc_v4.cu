@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "rq_rows.cuh"
 
 namespace hv {
 namespace {
@@ -210,6 +211,22 @@ __device__ __forceinline__ void warp_store_rows(const float (&src)[D], uint32_t 
   __syncwarp();
 }
 
+#ifdef HV_TC_INSTRUMENT
+// clock64 timeline of block 0 (tools/ts_show.py): who 0 = lane 0 of the first epilogue warp, who 1 = the MMA issuer
+__device__ uint32_t g_ts4[2][2 * 512];
+__device__ uint32_t g_ts4_n[2];
+#define HV4_STAMP(who, code)                                              \
+  do {                                                                    \
+    if (blockIdx.x == 0 && ts_n < 500) {                                  \
+      g_ts4[who][2 * ts_n] = (code);                                      \
+      g_ts4[who][2 * ts_n + 1] = static_cast<uint32_t>(clock64());        \
+      ++ts_n;                                                             \
+    }                                                                     \
+  } while (0)
+#else
+#define HV4_STAMP(who, code) do { } while (0)
+#endif
+
 template <int NWG>
 struct Roles {
   static constexpr int kEpiWarps = NWG * 4;
@@ -275,6 +292,7 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
   uint32_t* cnt_a_ready = reinterpret_cast<uint32_t*>(bar_acc_full + kMaxWg);  // [kMaxWg] warp arrivals: 4 per staged level
   uint32_t* cnt_acc_empty = cnt_a_ready + kMaxWg;                              // [kMaxWg] warp arrivals: 4 per drained unit
   uint32_t* s_tmem = cnt_acc_empty + kMaxWg;
+  uint32_t* s_turn = s_tmem + 1;  // streamed images: units issued so far, in the global order tile 0 wg 0, tile 0 wg 1, tile 1 wg 0, ...
 
   const int warp = ptx::warp_index();
   const int lane = threadIdx.x & 31;
@@ -282,8 +300,9 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
   if (warp == R::kProducerWarp && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_b_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bar_b_empty[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bar_b_empty[s]), p.resident ? 1 : p.tiles_per_cta);  // (streamed: one commit per issuer)
     }
+    *s_turn = 0;
     for (int w = 0; w < kMaxWg; ++w) {
       ptx::mbar_init(ptx::smem_u32(&bar_acc_full[w]), 1);
       cnt_a_ready[w] = 0;
@@ -330,7 +349,9 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
     const uint32_t scratch = ptx::smem_u32(a_hi);   // transpose scratch = this warpgroup's A buffer (see above)
     const int row0 = quarter * 32;                  // first tile row of this warp
 
+    [[maybe_unused]] int ts_n = threadIdx.x == 0 ? 0 : 100000;
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+      HV4_STAMP(0, 1);
       const int64_t warp_row0 = (tpc * grp + w) * kTileRows + row0;  // global row of the warp's local row 0
       const int64_t row = warp_row0 + lane;
       const bool valid = row < a.n;
@@ -344,10 +365,12 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
           warp_store_rows<D>(r, scratch, row0, lane,
                              [&](int lr) { return warp_row0 + lr < a.n ? base + (warp_row0 + lr) * D : nullptr; });
         }
+        HV4_STAMP(0, 2);
         stage_a_operand<D>(a_hi, a_lo, row_in_tile, r);
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::counter_add_release(cnt_ready, 1);
+        HV4_STAMP(0, 3);
 
         float best = -INFINITY;
         int best_k = 0;
@@ -358,15 +381,31 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
             ptx::mbar_wait(bar_full, acc_phase);
             acc_phase ^= 1;
             ptx::tc_fence_after_sync();
-            for (int c = 0; c < n_chunks; ++c) {
-              uint32_t v[32];
-              ptx::tmem_ld_32x32(acc_addr + c * 32, v);
-              ptx::tmem_wait_ld(v);
-              scan_chunk(v, t * p.ntile + col0 + c * 32, best, best_k);
+            if (t < 3 || t + 1 == p.n_ktiles) HV4_STAMP(0, 5);
+            if (R::kAccCols == 256 && n_chunks == 8) {
+              // A whole 256-column unit in one branch-free 2-D fold (rq_rows.cuh: pipelined 8-column loads, maxima per column
+              // class and per chunk, the maximiser located once per unit).  The chunk-by-chunk form below votes and, early in a
+              // level, re-scans most chunks: 2100 cycles per unit against the 1664 the other warpgroup's MMAs take, which left
+              // the tensor pipe idle for 30 % of a tile (clock64 timeline, tools/v4_timeline.sh).
+              float m;
+              int c;
+              rows::scan_x8_pairs<32>(acc_addr, m, c);
+              if (m > best) {  // strict: an earlier unit keeps exact ties
+                best = m;
+                best_k = t * p.ntile + col0 + c;
+              }
+            } else {
+              for (int c = 0; c < n_chunks; ++c) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(acc_addr + c * 32, v);
+                ptx::tmem_wait_ld(v);
+                scan_chunk(v, t * p.ntile + col0 + c * 32, best, best_k);
+              }
             }
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::counter_add_release(cnt_empty, 1);
+            if (t < 3 || t + 1 == p.n_ktiles) HV4_STAMP(0, 6);
           }
         }
         best_k = min(best_k, a.k - 1);
@@ -377,6 +416,7 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
         warp_load_rows<D>(e, scratch, row0, lane, [&](int lr) {
           return cb + static_cast<int64_t>(__shfl_sync(0xffffffffu, best_k, lr)) * D;
         });
+        HV4_STAMP(0, 7);
         const float ll = rq_level_tail_o<D, ROT>(r, e, a.beta, o);
         if (a.emb_out != nullptr) {
           float* base = a.emb_out + static_cast<int64_t>(l) * a.n * D;
@@ -389,11 +429,15 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
           if (a.level_loss != nullptr) a.level_loss[static_cast<int64_t>(l) * a.n + row] = ll;
         }
       }
+      HV4_STAMP(0, 8);
       if (valid && a.loss != nullptr) a.loss[row] = total_loss;
       if (a.final_residual != nullptr)
         warp_store_rows<D>(r, scratch, row0, lane,
                            [&](int lr) { return warp_row0 + lr < a.n ? a.final_residual + (warp_row0 + lr) * D : nullptr; });
     }
+#ifdef HV_TC_INSTRUMENT
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_ts4_n[0] = ts_n;
+#endif
     }  // else: warpgroup without a row tile (small N: fewer tiles per CTA so that more SMs work)
   } else {
     ptx::setmaxnreg_dec<R::kHelperRegs>();
@@ -424,7 +468,7 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
         }
       }
     }
-    } else if (warp == R::kMmaWarp) {
+    } else if (warp == R::kMmaWarp || (!p.resident && warp == R::kMmaWarp + 1 && p.tiles_per_cta > 1)) {
     // ===================================== MMA issuer =====================================================
     const uint32_t ones = ptx::smem_u32(s_ones);
     if (p.resident) {
@@ -490,44 +534,63 @@ __global__ void __launch_bounds__(Roles<NWG>::kThreads, 1) rq_fwd_tc_kernel(RqFw
       }
       __syncwarp();
     } else {
-      // Streamed operand images: all warpgroups consume the same stage in lock step (one load serves tpc tiles).
-      uint32_t it = 0;
-      uint32_t levels_seen[kMaxWg] = {0, 0, 0, 0};
-      uint32_t acc_uses[kMaxWg] = {0, 0, 0, 0};
+      // Streamed operand images: all warpgroups consume the same stage in lock step (one load serves tpc tiles), unit after
+      // unit in the order tile t wg 0, tile t wg 1, tile t + 1 wg 0 ...  ONE ISSUER WARP PER WARPGROUP: tcgen05.mma blocks its
+      // thread while the queue is full, i.e. for about the execution time of the unit, and the bookkeeping between two units
+      // (stage barrier, accumulator counter, descriptors, commit: ~1000 cycles measured) used to run when the queue had
+      // drained -- the tensor pipe idled 22 % of a tile.  Now issuer w does its waiting while the other issuer's MMAs are
+      // being pushed, and takes its turn (s_turn) the moment they are all queued.  (streamed plans run two warpgroups.)
+      static_assert(kMaxWg >= 2, "two issuers");
+      const int w = warp - R::kMmaWarp;          // this issuer's warpgroup
+      const uint32_t n_issuers = static_cast<uint32_t>(tpc);
+      uint32_t it = 0, levels_seen = 0, acc_uses = 0;
+      [[maybe_unused]] int ts_n = (lane == 0 && w == 0) ? 0 : 100000;
       for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         for (int tile = 0; tile < total_tiles; ++tile, ++it) {
           const int t = tile % p.n_ktiles;
           const int s = it % p.stages;
+          if (t < 3) HV4_STAMP(1, 20);
           ptx::mbar_wait(ptx::smem_u32(&bar_b_full[s]), (it / p.stages) & 1);
+          if (t < 3) HV4_STAMP(1, 21);
           const uint32_t b_tile = ptx::smem_u32(s_b + static_cast<size_t>(s) * p.tile_bytes);
-          for (int w = 0; w < tpc; ++w) {
-            if (t == 0) {
-              levels_seen[w]++;
-              ptx::counter_wait(ptx::smem_u32(&cnt_a_ready[w]), 4 * levels_seen[w]);
+          if (t == 0) {
+            levels_seen++;
+            ptx::counter_wait(ptx::smem_u32(&cnt_a_ready[w]), 4 * levels_seen);
+          }
+          for (int u = 0; u < units_per_tile; ++u) {
+            ptx::counter_wait(ptx::smem_u32(&cnt_acc_empty[w]), 4 * acc_uses);
+            acc_uses++;
+            ptx::counter_wait(ptx::smem_u32(s_turn), (it * units_per_tile + u) * n_issuers + w);  // my turn
+            ptx::tc_fence_after_sync();
+            if (t < 3) HV4_STAMP(1, 22 + w);
+            if (ptx::elect_one()) {
+              const int col0 = u * R::kAccCols;
+              const uint32_t a_hi = ptx::smem_u32(s_a + w * p.a_bytes);
+              issue_unit<D>(tmem_base + w * R::kAccCols, a_hi, a_hi + p.a_bytes / 2, ones, b_tile, p.ntile, col0,
+                            min(R::kAccCols, p.ntile - col0), ptx::smem_u32(&bar_acc_full[w]));
             }
-            for (int u = 0; u < units_per_tile; ++u) {
-              ptx::counter_wait(ptx::smem_u32(&cnt_acc_empty[w]), 4 * acc_uses[w]);
-              acc_uses[w]++;
-              ptx::tc_fence_after_sync();
-              if (ptx::elect_one()) {
-                const int col0 = u * R::kAccCols;
-                const uint32_t a_hi = ptx::smem_u32(s_a + w * p.a_bytes);
-                issue_unit<D>(tmem_base + w * R::kAccCols, a_hi, a_hi + p.a_bytes / 2, ones, b_tile, p.ntile, col0,
-                              min(R::kAccCols, p.ntile - col0), ptx::smem_u32(&bar_acc_full[w]));
-              }
-              __syncwarp();
-            }
+            __syncwarp();
+            if (lane == 0) ptx::counter_add_release(ptx::smem_u32(s_turn), 1u);
           }
           if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&bar_b_empty[s]));
           __syncwarp();
+          if (t < 3) HV4_STAMP(1, 26);
         }
       }
+#ifdef HV_TC_INSTRUMENT
+      if (blockIdx.x == 0 && lane == 0 && w == 0) g_ts4_n[1] = ts_n;
+#endif
     }
     }
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+#ifdef HV_TC_INSTRUMENT
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int who = 0; who < 2; ++who)
+      for (uint32_t i = 0; i < g_ts4_n[who] && i < 500; ++i) printf("TS %d %u %u\n", who, g_ts4[who][2 * i], g_ts4[who][2 * i + 1]);
+#endif
   if (warp == R::kMmaWarp) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, kTmemCols);

@@ -116,10 +116,15 @@ __device__ __forceinline__ void scan_unit_x16(uint32_t t0, float& m_out, int& co
 // Location of the maximiser from the fold over 8 classes x NC chunks (shared by the 8-column scans).
 template <int NC>
 __device__ __forceinline__ void locate_8(uint32_t t0, const float (&g)[8], const float (&cm)[NC], float& m_out, int& col_out) {
-  static_assert(NC == 8 || NC == 16, "64 or 128 columns");
-  float m = max3(max3(cm[0], cm[1], cm[2]), max3(cm[3], cm[4], cm[5]), fmaxf(cm[6], cm[7]));
-  if constexpr (NC == 16)
-    m = max3(m, max3(max3(cm[8], cm[9], cm[10]), max3(cm[11], cm[12], cm[13]), fmaxf(cm[14], cm[15])), m);
+  static_assert(NC == 8 || NC == 16 || NC == 32, "64, 128 or 256 columns");
+  float m8[NC / 8];
+#pragma unroll
+  for (int i = 0; i < NC / 8; ++i)
+    m8[i] = max3(max3(cm[8 * i], cm[8 * i + 1], cm[8 * i + 2]), max3(cm[8 * i + 3], cm[8 * i + 4], cm[8 * i + 5]), fmaxf(cm[8 * i + 6], cm[8 * i + 7]));
+  float m = m8[0];
+#pragma unroll
+  for (int i = 1; i < NC / 8; ++i) m = fmaxf(m, m8[i]);
+  // class of the maximiser: sum_j [g_j == m] * (16 + j);  chunk: sum_c [cm_c == m] * (NC + c)   (FMA pipe)
   float s2[2] = {0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -130,14 +135,14 @@ __device__ __forceinline__ void locate_8(uint32_t t0, const float (&g)[8], const
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const float e = __saturatef(fmaf(cm[c] - m, kBig, 1.0f));
-    c4[c & 3] = fmaf(e, static_cast<float>(16 + c), c4[c & 3]);
+    c4[c & 3] = fmaf(e, static_cast<float>(NC + c), c4[c & 3]);
   }
   const float cls = s2[0] + s2[1];
   const float chk = (c4[0] + c4[1]) + (c4[2] + c4[3]);
-  // one class: 16..23, two or more: >= 33; one chunk: 16..31, two or more: >= 33
-  const bool unique = (cls < 32.f && chk < 32.f) || m < -1e29f;
+  // one class: 16..23, two or more: >= 33; one chunk: NC..2 NC - 1, two or more: >= 2 NC + 1
+  const bool unique = (cls < 32.f && chk < static_cast<float>(2 * NC)) || m < -1e29f;
   float best = m;
-  int col = 8 * (static_cast<int>(chk) - 16) + static_cast<int>(cls) - 16;
+  int col = 8 * (static_cast<int>(chk) - NC) + static_cast<int>(cls) - 16;
   if (__any_sync(0xffffffffu, !unique)) {
     best = -INFINITY;
     col = 0;
