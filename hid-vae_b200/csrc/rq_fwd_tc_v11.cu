@@ -304,8 +304,10 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
           // the row-owner layout (32x32b), read back in the accumulator-fragment layout (16x256b), so that a quad of lanes
           // stores one full 32-byte sector of a row; thread-per-row 16-byte stores touch 32 lines per instruction
           // (measured 1.25 -> 1.16 ms on the 4 Mi-row training forward).  Warp-collective: every lane takes part.
+          stamp(10);
           float o[D];
           const float ll = rq_level_tail_o<D, ROT>(r, e, a.beta, o);
+          stamp(11);
           if (a.emb_out != nullptr) {
             uint32_t ob[32];
 #pragma unroll
@@ -313,6 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) rq_fwd_tc_v11_kernel(RqFwdArgs a,
             ptx::tmem_st_32x32(a_tmem + lane_bits, ob);
             ptx::tmem_wait_st();
             __syncwarp();
+            stamp(12);
             float* out_l = a.emb_out + (static_cast<int64_t>(l) * a.n + tile_row0(i) + q * 32) * D + 2 * (lane & 3);
             const int64_t rows_left = a.n - (tile_row0(i) + q * 32);
 #pragma unroll
