@@ -7,7 +7,7 @@
 // mbarriers, the code gather through L2 -- with only 3-4 tiles in flight.  This generation removes the hand-overs
 // instead of speeding them up:
 //
-//   OWNERSHIP  four warpgroups, each owns one row tile for its L levels; thread t of the warpgroup owns row t (= TMEM
+//   OWNERSHIP  three warpgroups, each owns one row tile for its L levels; thread t of the warpgroup owns row t (= TMEM
 //              lane t) in registers from the x load to the last id.  There is no row group / scan group split, no
 //              candidate table, no second layout.
 //   A IN TMEM  the residual's bf16 hi / lo halves are written by their owner with tcgen05.st into 32 TMEM columns of
@@ -17,14 +17,19 @@
 //              because A no longer lives there), rows XOR-swizzled by 16-byte chunk, so the chosen code row is eight
 //              LDS.128 instead of a round trip to L2.
 //   ISSUER     a level is two units of 128 codes (3*D/16 tcgen05.mma from TMEM + 1 from the constant ones block, one
-//              commit each).  A tcgen05.mma takes as long to issue as the previous one takes to execute (measured: 80
-//              cycles each), so a seventeenth warp does nothing else: warpgroups queue "level staged" requests, the
-//              issuer serves them first come first served, giving every unit the next of three 128-column accumulators
-//              (unit number % 3) as soon as its previous user has been scanned.  The scan of unit 0 overlaps the MMAs
-//              of unit 1 and of other tiles, and no scanning warp ever waits inside an issue loop (which, with the
-//              owners issuing for themselves, held accumulators hostage: measured 9000 cycles per level).
-//   SCAN       by the row's owner: 2-D fold with 3-input maxima over 16-column loads, exact
-//              first-index path when a row has more than one maximiser; the id stays in a register.
+//              commit each).  tcgen05.mma blocks its thread while the MMA queue is full, so a thirteenth warp does
+//              nothing else: warpgroups queue "level staged" requests, the issuer serves them first come first served,
+//              giving every unit the next of three 128-column accumulators (unit number % 3) as soon as its previous
+//              user has been scanned.  The scan of unit 0 overlaps the MMAs of unit 1 and of other tiles, and no
+//              scanning warp ever waits inside an issue loop (which, with the owners issuing for themselves, held
+//              accumulators hostage: measured 9000 cycles per level).
+//   WAITS      every wait is a hardware-parked mbarrier wait (a completion barrier per (warpgroup, unit), a "scanned"
+//              barrier per accumulator, a doorbell for the request queue).  The first builds polled shared-memory
+//              counters: the poll loops were 15 % of all issued instructions and took issue slots from the scanning
+//              warps (4 Mi-row encode 0.725 -> 0.61 ms when they went).
+//   SCAN       by the row's owner: 2-D fold (maxima per column class and per chunk, 3-input maxima) over pipelined
+//              8-column loads (rq_rows.cuh), exact first-index path when a row has more than one maximiser; the id
+//              stays in a register.
 //   score[row, k] = r.c_k - |c_k|^2 / 2 with the bf16 3-way split exactly as in the other generations
 //   (modules/quantize.py:108-122); only ids (and emb_out / loss in training) leave the SM.
 #include <stdlib.h>

@@ -16,9 +16,13 @@
 //   link latency-bound, so throughput comes from the NUMBER OF ROW TILES IN FLIGHT per SM: the persistent CTA runs
 //   NWG epilogue warpgroups (4 where shared memory allows, else 2), each owning one 128-row tile and one
 //   512/NWG-column fp32 accumulator in TMEM; a level's N tile is processed in units of at most that many columns.
-//   One more warp is the TMA producer, one allocates TMEM and issues every tcgen05.mma, serving whichever
-//   warpgroup is ready first.  Epilogue thread t owns row t of its tile for all L levels: tcgen05.ld (32x32b)
-//   hands it whole rows, the running (max, argmax) stays in registers, then the warp gathers the fp32 code rows,
+//   One more warp is the TMA producer, one allocates TMEM and issues the tcgen05.mma -- resident images: serving whichever
+//   warpgroup is ready first; streamed images (C4): one issuer warp PER warpgroup, taking turns, so that an issuer's
+//   bookkeeping between two units overlaps the other issuer's MMAs (tcgen05.mma blocks its thread while the queue is
+//   full) and the scan of one warpgroup's unit always hides behind the other warpgroup's MMAs.
+//   Epilogue thread t owns row t of its tile for all L levels: a whole 256-column unit is scanned by the branch-free
+//   2-D fold of rq_rows.cuh (other unit widths: chunk by chunk with tcgen05.ld 32x32b), the running (max, argmax) stays
+//   in registers, then the warp gathers the fp32 code rows,
 //   forms emb_out / loss / the next residual in registers and re-stages the residual (bf16 hi/lo) as the next
 //   level's A operand.  The [N, K] score matrix never leaves the SM.
 #include <stdlib.h>
