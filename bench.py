@@ -147,7 +147,7 @@ class ClockSampler:
         time.sleep(0.12)
         self.proc.terminate()
         rows = [r for (ts, r) in self.rows if t0 - 0.05 <= ts <= t1 + 0.05] or [r for (_, r) in self.rows]
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
@@ -155,10 +155,13 @@ class ClockSampler:
                 for nme, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
+                power.append(float(r[2]))
             except Exception:
                 pass
+        # (the fused encoder runs the board at its power limit: SM clocks of 1.3-1.5 GHz under this step are the power cap at work,
+        # whether or not a 50 ms sample happens to catch the sw_power_cap flag; the power draw is reported beside it)
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(smax) if smax else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), power_w_max=max(power) if power else None)
 
 
 def bind_host_memory_near(local_rank):
