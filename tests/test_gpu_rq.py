@@ -343,8 +343,11 @@ def test_backward_broadcast_grad(ops):
 # ---------------------------------------------------------------------------------------------------------------
 # full-size, size-independent properties (BASELINE.json configs 4 and 5 shapes)
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(65536, 64, 4096, 4), (1 << 20, 32, 256, 3)], ids=["config4", "config5_chunk"])
+@pytest.mark.parametrize("shape", [(65536, 64, 4096, 4), (1 << 20, 32, 256, 3), (38000 + 77, 64, 1500, 2)],
+                         ids=["config4", "config5_chunk", "streamed_two_tiles_per_cta_ragged"])
 def test_full_size_properties(ops, shape):
+    """(the third shape: streamed operand images with two row tiles per CTA and one MMA issuer per warpgroup, an odd number
+    of row tiles -- the last group's second tile is empty --, a ragged last tile and a padded last operand image)"""
     n, d, k, L = shape
     x = _dev(unit_rows(n, d, seed=41))
     cbs = _dev(make_codebooks(L, k, d, seed=42))
