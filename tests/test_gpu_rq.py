@@ -435,3 +435,22 @@ def test_resident_kernel_many_tiles_per_warpgroup(ops, training):
     bad = torch.nonzero(~same).view(-1)[:512].cpu()
     if bad.numel():
         check_ids(a.ids[bad.cuda()], x[bad.cuda()].cpu(), cbs.cpu(), O.MODE_ROTATION_TRICK, 0.4, bool(training))
+
+
+@pytest.mark.parametrize("shape", [(300000, 32, 256, 3), (40000, 64, 1500, 2)], ids=["row_owner_kernel", "streamed_kernel"])
+def test_repeated_launches_are_bit_identical(ops, shape):
+    """The forward kernels hand tiles, accumulators and turns around through barriers: twelve launches on the same rows must
+    give the same ids (both kernels) and the same emb_out / loss bit for bit -- any race in the hand-overs would show up here."""
+    n, d, k, L = shape
+    x = _dev(unit_rows(n, d, seed=71))
+    cbs = _dev(make_codebooks(L, k, d, seed=72))
+    packed = ops.pack_codebooks(cbs)
+    ids0 = ops.rq_encode(x, cbs, packed=packed).clone()
+    out0 = ops.rq_forward(x, cbs, O.MODE_ROTATION_TRICK, True, 0.4, want_emb=True, want_loss=True, packed=packed)
+    emb0, loss0, tids0 = out0.emb_out.clone(), out0.loss.clone(), out0.ids.clone()
+    assert torch.equal(tids0[:, 0], ids0[:, 0])   # (later levels differ by design: training subtracts the rotated value)
+    for it in range(12):
+        assert torch.equal(ops.rq_encode(x, cbs, packed=packed), ids0), f"encode, launch {it}"
+        out = ops.rq_forward(x, cbs, O.MODE_ROTATION_TRICK, True, 0.4, want_emb=True, want_loss=True, packed=packed)
+        assert torch.equal(out.ids, tids0), f"training ids, launch {it}"
+        assert torch.equal(out.emb_out, emb0) and torch.equal(out.loss, loss0), f"training values, launch {it}"
