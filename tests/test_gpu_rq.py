@@ -454,3 +454,24 @@ def test_repeated_launches_are_bit_identical(ops, shape):
         out = ops.rq_forward(x, cbs, O.MODE_ROTATION_TRICK, True, 0.4, want_emb=True, want_loss=True, packed=packed)
         assert torch.equal(out.ids, tids0), f"training ids, launch {it}"
         assert torch.equal(out.emb_out, emb0) and torch.equal(out.loss, loss0), f"training values, launch {it}"
+
+
+@pytest.mark.parametrize("cfg", [(32, 256, 3), (64, 1500, 2)], ids=["row_owner_kernel", "streamed_kernel"])
+def test_row_counts_around_tile_and_wave_boundaries(ops, cfg):
+    """Row counts around one tile, the three tiles a CTA keeps in flight, one wave of 148 CTAs and the switch from one to two
+    (streamed kernel) / three (row-owner kernel) tiles per CTA: the tensor-core ids must match the exact-fp32 CUDA-core kernel
+    on (almost) every row, and rows beyond n must never be written."""
+    d, k, L = cfg
+    cbs = _dev(make_codebooks(L, k, d, seed=81))
+    packed = ops.pack_codebooks(cbs)
+    wave = 148 * 128
+    for n in (1, 2, 127, 128, 129, 255, 257, 383, 385, 512, wave - 1, wave, wave + 1, 2 * wave + 5, 3 * wave + 127, 4 * wave - 129):
+        x = _dev(unit_rows(n, d, seed=n % 1000))
+        table = torch.full((n + 3, L), -7, dtype=torch.int64, device="cuda")
+        ops.rq_encode(x, cbs, packed=packed, ids_out=table[:n])
+        assert bool((table[n:] == -7).all()), n
+        ids = table[:n]
+        assert int(ids.min()) >= 0 and int(ids.max()) < k, n
+        ref = ops.rq_encode(x, cbs, algo="simt")
+        agree = float((ids == ref).all(dim=1).float().mean())
+        assert agree >= (0.998 if n > 1000 else 0.97), (n, agree)
