@@ -519,7 +519,7 @@ def run_train_dp(rank, world, dev):
         def step():   # the eager step: what a line-by-line port of train_hidvae.py:700-770 costs (launch-bound)
             grads.zero()
             out = model(fetch(torch.randint(0, n_items, (bs,), device=dev, generator=g)), gumbel_t=0.2)
-            out.loss.backward()
+            grads.backward(out.loss)
             grads.all_reduce()
             opt.step()
             last["loss"] = out.loss.detach()   # (a live autograd graph would pin AccumulateGrad nodes to this stream)

@@ -40,13 +40,33 @@ class FlatGradAllReduce:
         total = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            self.views.append(self.flat[off: off + p.numel()].view_as(p))
+            p.grad = self.views[-1]
             off += p.numel()
 
     def zero(self) -> None:
         self.flat.zero_()
+
+    def backward(self, loss: torch.Tensor) -> None:
+        """`loss.backward()` with the gradients ADDED to the flat buffer by one multi-tensor kernel.  A plain backward() on
+        parameters whose `.grad` is a view costs one `add_` launch per parameter (autograd accumulates into a defined grad:
+        176 launches of 1.7 us in a HiD-VAE step, 9 % of the step at batch 128); here the grads are detached first, autograd
+        hands over its freshly computed tensors, and `_foreach_add_` folds them into the views, which are then bound again
+        (optimizer, all_reduce and check_views see the same views as before; parameters without a gradient keep zeros)."""
+        for p in self.params:
+            p.grad = None
+        loss.backward()
+        dst, src = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is not None:
+                dst.append(v)
+                src.append(p.grad)
+            p.grad = v
+        if dst:
+            torch._foreach_add_(dst, src)
 
     def check_views(self) -> None:
         """autograd / optimizers that set grads to None would silently detach a parameter from the flat buffer."""

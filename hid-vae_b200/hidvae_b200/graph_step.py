@@ -54,7 +54,7 @@ class GraphedTrainStep:
             batch = fetch(self.idx)
             with torch.autocast("cuda", dtype=autocast_dtype or torch.bfloat16, enabled=autocast_dtype is not None):
                 out = model(batch, gumbel_t=gumbel_t)
-            (out.loss / loss_divisor).backward()
+            grads.backward(out.loss / loss_divisor)   # (one multi-tensor add into the flat buffer, not an add_ per parameter)
             self.stats.copy_(step_statistics(out))
             self.emb_norms.copy_(out.embs_norm.mean(dim=0))
 

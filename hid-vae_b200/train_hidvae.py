@@ -315,7 +315,7 @@ def train(
                     batch = train_dataset[torch.randint(0, n_train, (batch_size,), device=device, generator=gen)]
                     with torch.autocast("cuda", dtype=torch.float16 if mixed_precision_type == "fp16" else torch.bfloat16, enabled=bool(amp)):
                         out = model(batch, gumbel_t=t)
-                    scaler.scale(out.loss / gradient_accumulate_every).backward()
+                    grads.backward(scaler.scale(out.loss / gradient_accumulate_every))
                 grads.all_reduce()                # (scaled) gradients first: every rank then sees the same inf / nan verdict
                 scaler.unscale_(optimizer)
                 scaler.step(optimizer)

@@ -221,3 +221,30 @@ def test_tokenizer_cached_consumers_match_reference_golden(golden_dir):
         # ids beyond the cache read row 0 (h_semids.py:251-252)
         far = torch.tensor([[0, 10 ** 6]])
         assert torch.equal(tok._tokenize_seq_batch_from_cached(far)[0, tok.sem_ids_dim:], tok.cached_ids[0])
+
+
+def test_flat_gradient_backward_adds_like_autograd_accumulation():
+    """FlatGradAllReduce.backward (detach the grads, backward, one multi-tensor add into the views) against autograd's own
+    accumulation into the views: two micro-steps, a parameter that receives no gradient, views bound again afterwards."""
+    from hidvae_b200 import dist as hv
+
+    def build():
+        torch.manual_seed(3)
+        m = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+        unused = torch.nn.Parameter(torch.ones(4))
+        return m, unused
+
+    data = torch.randn(2, 8, 6, generator=torch.Generator().manual_seed(5))
+    flats = []
+    for use_backward in (False, True):
+        m, unused = build()
+        grads = hv.FlatGradAllReduce(list(m.parameters()) + [unused])
+        grads.zero()
+        for k in range(2):
+            loss = m(data[k]).pow(2).mean()
+            grads.backward(loss) if use_backward else loss.backward()
+        grads.check_views()
+        assert float(unused.grad.abs().max()) == 0.0
+        flats.append(grads.flat.clone())
+    torch.testing.assert_close(flats[1], flats[0], rtol=1e-6, atol=1e-7)
+    assert float(flats[0].abs().max()) > 0

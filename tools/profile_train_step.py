@@ -36,7 +36,7 @@ def step():
     idx = torch.randint(0, n, (bs,), device=dev, generator=g)
     grads.zero()
     out = model(TaggedSeqBatch(None, None, None, x[idx], None, None, tags_emb[idx], tags_idx[idx]), gumbel_t=0.2)
-    out.loss.backward()
+    grads.backward(out.loss)
     opt.step()
 
 
