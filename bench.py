@@ -758,7 +758,8 @@ def run_reference(args):
                              ms_per_step=dt / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                              dtype="f32", data="synthetic",
                              config=dict(WORKLOAD, parallelism="cpu", items_per_gpu_per_step=REF_SAMPLE_ITEMS, chunk_items=512,
-                                         encoder_precision="fp32"),
+                                         encoder_precision="fp32",
+                                         l2_between_steps="n/a (host arm: a bounded sample of the same catalogue per step)"),
                              impl="reference", cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
                              e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
