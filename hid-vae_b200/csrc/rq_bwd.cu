@@ -329,9 +329,18 @@ __global__ void __launch_bounds__(kBwd2Threads, 2) rq_bwd_smem_kernel(RqBwdArgs 
 // scalars -- shuffle reductions, three reciprocal norms, the rotation coefficients -- that every lane of a row repeats.
 // With half as many lanes per row each of those warp instructions serves twice as many rows and a reduction is one shuffle
 // shorter.  Registers: the chosen code rows are read from shared memory a second time in the backward sweep instead of
-// being kept (2 LDS.128 per level), so the kernel still runs 2 CTAs x 256 threads per SM.
+// being kept (2 LDS.128 per level).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kBwd8Threads = 256;
+// One CTA of 384 threads per SM, i.e. 168 registers per thread: nothing spills and the compiler keeps more of the chain in
+// registers.  Measured at 4 Mi rows (D = 32, L = 3): 2 x 256 threads (128 registers, 56 B of spills) 0.708 ms, 1 x 320 0.687,
+// 1 x 352 0.637, 1 x 384 0.600, 1 x 416 / 448 (152 / 144 registers) 0.84, 1 x 512 0.696, 2 x 320 1.19, 3 x 192 1.89.
+#ifndef HV_BWD8_THREADS
+#define HV_BWD8_THREADS 384
+#endif
+#ifndef HV_BWD8_CTAS
+#define HV_BWD8_CTAS 1
+#endif
+constexpr int kBwd8Threads = HV_BWD8_THREADS;
 
 struct F8 {
   float v[8];
@@ -356,7 +365,7 @@ __device__ __forceinline__ float dot8(const F8& a, const F8& b) {
 }
 
 template <int D, bool ROT, bool TRAIN, int NL>
-__global__ void __launch_bounds__(kBwd8Threads, 2) rq_bwd_smem8_kernel(RqBwdArgs a) {
+__global__ void __launch_bounds__(kBwd8Threads, HV_BWD8_CTAS) rq_bwd_smem8_kernel(RqBwdArgs a) {
   constexpr int LPR = D / 8;
   constexpr int ROWS_PER_WARP = 32 / LPR;
   constexpr bool rot = ROT && TRAIN;
@@ -529,7 +538,7 @@ int launch_d(const RqBwdArgs& a, bool rot, cudaStream_t stream) {
   };
   auto go8 = [&](auto kernel) -> int {
     if (int st = prepare_kernel(kernel, 0, smem_bytes)) return st;
-    kernel<<<2 * props.sm_count, kBwd8Threads, smem_bytes, stream>>>(a);
+    kernel<<<HV_BWD8_CTAS * props.sm_count, kBwd8Threads, smem_bytes, stream>>>(a);
     HV_CUDA_CHECK(cudaGetLastError());
     return HV_OK;
   };
