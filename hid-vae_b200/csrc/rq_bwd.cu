@@ -190,19 +190,24 @@ __global__ void __launch_bounds__(kBwdThreads, NL > 0 ? HV_BWD_MINB : 1) rq_bwd_
 // ---------------------------------------------------------------------------------------------------------------------
 // Large-N variant for codebooks that fit in shared memory (L K D 4 <= 96 KB: every HiD-VAE config).  Same arithmetic, two
 // changes that remove the memory latency the kernel above exposes per row (ncu: stall_long_scoreboard 39 % of warp time):
-//   * the fp32 codebooks are staged in shared memory once per persistent CTA (2 CTAs per SM): the id -> code row gather
+//   * the fp32 codebooks are staged in shared memory once per persistent CTA: the id -> code row gather
 //     is an LDS.128 instead of a dependent round trip to L2 (and 4 L D bytes per row less L2 traffic);
 //   * the row's inputs (x, ids, g_emb, g_loss) are loaded ONE ITERATION AHEAD into registers, so no load of the current
 //     row is ever waited for.
 // ---------------------------------------------------------------------------------------------------------------------
+// (one CTA of 512 threads per SM: STE training backward at 4 Mi rows 0.674 ms at 2 x 320 threads, 0.642 at 1 x 384, 0.600 at
+// 1 x 512; the eight-floats-per-lane kernel below measures 0.708 on this chain -- it pays off where the per-row scalars dominate)
 #ifndef HV_BWD2_THREADS
-#define HV_BWD2_THREADS 320
+#define HV_BWD2_THREADS 512
+#endif
+#ifndef HV_BWD2_CTAS
+#define HV_BWD2_CTAS 1
 #endif
 constexpr int kBwd2Threads = HV_BWD2_THREADS;
 constexpr int kBwd2SmemLimit = 96 * 1024;
 
 template <int D, bool ROT, bool TRAIN, int NL>
-__global__ void __launch_bounds__(kBwd2Threads, 2) rq_bwd_smem_kernel(RqBwdArgs a) {
+__global__ void __launch_bounds__(kBwd2Threads, HV_BWD2_CTAS) rq_bwd_smem_kernel(RqBwdArgs a) {
   constexpr int LPR = D / 4;
   constexpr int ROWS_PER_WARP = 32 / LPR;
   constexpr bool rot = ROT && TRAIN;
@@ -532,7 +537,7 @@ int launch_d(const RqBwdArgs& a, bool rot, cudaStream_t stream) {
   const int smem_bytes = a.n_levels * a.k * D * 4;
   auto go2 = [&](auto kernel) -> int {
     if (int st = prepare_kernel(kernel, 0, smem_bytes)) return st;
-    kernel<<<2 * props.sm_count, kBwd2Threads, smem_bytes, stream>>>(a);
+    kernel<<<HV_BWD2_CTAS * props.sm_count, kBwd2Threads, smem_bytes, stream>>>(a);
     HV_CUDA_CHECK(cudaGetLastError());
     return HV_OK;
   };

@@ -58,6 +58,8 @@ if "rq" in args.what or "train" in args.what:
         tf = ms(lambda: ops.rq_forward(x, cbs, 3, True, 0.4, want_emb=True, want_loss=True, packed=packed))
         tb = ms(lambda: ops.rq_backward(x, cbs, out.ids, 3, True, 0.4, g_emb, g_loss, None))
         bf, bb = n * (4 * d + 4 * d * L + 8 * L + 4), n * (4 * d + 8 * L + 4 * d * L + 4 + 4 * d)
+        ids_e = ops.rq_encode(x, cbs, packed=packed)
+        res["bwd_ste_4Mi_ms"] = ms(lambda: ops.rq_backward(x, cbs, ids_e, ops.HV_MODE_STE, True, 0.4, g_emb, g_loss, None))
         res["train_4Mi"] = dict(fwd_ms=tf, bwd_ms=tb, fwd_gbs=bf / tf / 1e6, bwd_gbs=bb / tb / 1e6, both_gbs=(bf + bb) / (tf + tb) / 1e6)
     del x, g_emb
 if "c4" in args.what:
