@@ -511,9 +511,12 @@ __global__ void __launch_bounds__(kBwd8Threads, HV_BWD8_CTAS) rq_bwd_smem8_kerne
 
 // shapes the shared-memory variant serves: exact-level instantiation, codebooks within 96 KB, no per-level loss gradient,
 // and enough rows for 2 persistent CTAs per SM to amortise staging the codebooks
+#ifndef HV_BWD_SMEM_MIN_N
+#define HV_BWD_SMEM_MIN_N 65536
+#endif
 template <int D>
 bool bwd_smem_ok(const RqBwdArgs& a) {
-  return (D == 16 || D == 32 || D == 64) && a.n_levels >= 1 && a.n_levels <= 4 && a.g_level_loss == nullptr && a.n >= 65536 &&
+  return (D == 16 || D == 32 || D == 64) && a.n_levels >= 1 && a.n_levels <= 4 && a.g_level_loss == nullptr && a.n >= HV_BWD_SMEM_MIN_N &&
          static_cast<int64_t>(a.n_levels) * a.k * D * 4 <= kBwd2SmemLimit;
 }
 

@@ -62,6 +62,15 @@ if "rq" in args.what or "train" in args.what:
         res["bwd_ste_4Mi_ms"] = ms(lambda: ops.rq_backward(x, cbs, ids_e, ops.HV_MODE_STE, True, 0.4, g_emb, g_loss, None))
         res["train_4Mi"] = dict(fwd_ms=tf, bwd_ms=tb, fwd_gbs=bf / tf / 1e6, bwd_gbs=bb / tb / 1e6, both_gbs=(bf + bb) / (tf + tb) / 1e6)
     del x, g_emb
+if "small" in args.what:
+    for n in (1024, 12101, 32768):
+        x, cbs, g_emb, g_loss = bench.synth_rq(n, 32, 256, 3, 7, "cuda")
+        packed = ops.pack_codebooks(cbs)
+        out = ops.rq_forward(x, cbs, 3, True, 0.4, want_emb=True, want_loss=True, packed=packed)
+        res[f"small_{n}"] = dict(
+            enc_us=1e3 * ms(lambda: ops.rq_encode(x, cbs, packed=packed)),
+            fwd_us=1e3 * ms(lambda: ops.rq_forward(x, cbs, 3, True, 0.4, want_emb=True, want_loss=True, packed=packed)),
+            bwd_us=1e3 * ms(lambda: ops.rq_backward(x, cbs, out.ids, 3, True, 0.4, g_emb, g_loss, None)))
 if "c4" in args.what:
     n, d, k, L = 65536, 64, 4096, 4
     x, cbs, _g, _l = bench.synth_rq(n, d, k, L, 9, "cuda")
